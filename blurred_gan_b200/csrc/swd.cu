@@ -1,0 +1,295 @@
+// Sliced-Wasserstein evaluation kernels for sm_100a (everything except the sort, see sort.cu).
+//
+// Replaces the numpy/scipy arithmetic of the reference's sliced_wasserstein.py:
+//   pyr_down / pyr_up / Laplacian residual   :65-88   (5x5 binomial, REFLECT_101 border, fp64 accumulate)
+//   get_descriptors_for_minibatch            :13-23   (7x7xC patch gather, x/y transposed -- SURVEY Q10)
+//   finalize_descriptors                     :27-34   (per-channel mean / population std)
+//   np.matmul(A, dirs)                       :45-46   (fp32 projection onto unit directions)
+//   np.mean(np.abs(projA - projB))           :49-50
+#include "common.cuh"
+
+namespace bgan {
+namespace {
+
+// REFLECT_101 ("mirror" in scipy.ndimage): ... 2 1 | 0 1 2 ... n-1 | n-2 n-3 ...
+__device__ __forceinline__ int mirror101(int i, int n) {
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - i;
+}
+
+__constant__ double kB5[5] = {1.0, 4.0, 6.0, 4.0, 1.0};
+
+// y[p, oy, ox] = sum_{dy,dx} B5[dy] B5[dx] / 256 * x[p, m(2 oy + dy - 2), m(2 ox + dx - 2)]
+// Every product and partial sum is exact in fp64 (weights are small integers / 256, inputs fp32),
+// so the result is the correctly rounded exact value -- bit-identical to scipy's fp64 accumulation.
+__global__ void pyr_down_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int oh, int ow) {
+    const int64_t total = static_cast<int64_t>(planes) * oh * ow;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(idx % ow);
+        const int oy = static_cast<int>((idx / ow) % oh);
+        const int p = static_cast<int>(idx / (static_cast<int64_t>(ow) * oh));
+        const float* src = x + static_cast<size_t>(p) * H * W;
+        int cols[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) cols[d] = mirror101(2 * ox + d - 2, W);
+        double acc = 0.0;
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+            const float* row = src + static_cast<size_t>(mirror101(2 * oy + dy - 2, H)) * W;
+            double racc = 0.0;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) racc += kB5[dx] * static_cast<double>(__ldg(row + cols[dx]));
+            acc += kB5[dy] * racc;
+        }
+        y[idx] = static_cast<float>(acc * (1.0 / 256.0));
+    }
+}
+
+// y[p, Y, X] = (minuend ? minuend[p, Y, X] : 0) -/+ sum 4 B5 B5 / 256 * Z[m(Y+dy-2), m(X+dx-2)],
+// Z = x zero-stuffed to (2h, 2w): Z[2i, 2j] = x[i, j], zero elsewhere.
+__global__ void pyr_up_kernel(const float* __restrict__ x, const float* __restrict__ minuend, float* __restrict__ y, int planes,
+                              int h, int w) {
+    const int OH = 2 * h, OW = 2 * w;
+    const int64_t total = static_cast<int64_t>(planes) * OH * OW;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(idx % OW);
+        const int Y = static_cast<int>((idx / OW) % OH);
+        const int p = static_cast<int>(idx / (static_cast<int64_t>(OW) * OH));
+        const float* src = x + static_cast<size_t>(p) * h * w;
+        double acc = 0.0;
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+            const int zy = mirror101(Y + dy - 2, OH);
+            if (zy & 1) continue;
+            const float* row = src + static_cast<size_t>(zy >> 1) * w;
+            double racc = 0.0;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+                const int zx = mirror101(X + dx - 2, OW);
+                if (!(zx & 1)) racc += kB5[dx] * static_cast<double>(__ldg(row + (zx >> 1)));
+            }
+            acc += kB5[dy] * racc;
+        }
+        const float up = static_cast<float>(acc * (4.0 / 256.0));
+        y[idx] = minuend ? (minuend[idx] - up) : up;
+    }
+}
+
+// desc[m, c, i, j] = level[m / per_image, c, py[m] + j - half, px[m] + i - half]; per-channel sum / sum-of-squares
+template <int MAXC>
+__global__ void extract_kernel(const float* __restrict__ level, int C, int h, int w, const int32_t* __restrict__ px,
+                               const int32_t* __restrict__ py, int per_image, int nhood, int64_t n_desc,
+                               float* __restrict__ out, double* __restrict__ sums) {
+    const int half = nhood / 2;
+    const int per_chan = nhood * nhood;
+    const int dlen = C * per_chan;
+    const int64_t total = n_desc * dlen;
+    double s1[MAXC], s2[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) s1[c] = s2[c] = 0.0;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t m = idx / dlen;
+        const int k = static_cast<int>(idx - m * dlen);
+        const int c = k / per_chan;
+        const int ij = k - c * per_chan;
+        const int i = ij / nhood, j = ij - i * nhood;
+        const int64_t img = m / per_image;
+        const int row = __ldg(py + m) + j - half;
+        const int col = __ldg(px + m) + i - half;
+        const float v = __ldg(level + ((img * C + c) * h + row) * static_cast<int64_t>(w) + col);
+        out[idx] = v;
+#pragma unroll
+        for (int cc = 0; cc < MAXC; ++cc)
+            if (cc == c) {
+                s1[cc] += static_cast<double>(v);
+                s2[cc] += static_cast<double>(v) * static_cast<double>(v);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c >= C) break;
+        const double a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(sums + c, a);
+            atomicAdd(sums + C + c, b);
+        }
+    }
+}
+
+// desc = (desc - mean_c) / std_c, two fp32 operations like numpy's in-place `-=` then `/=`
+__global__ void normalise_kernel(float* __restrict__ desc, int64_t total, int C, int per_chan, const double* __restrict__ sums,
+                                 double count) {
+    __shared__ float s_mean[8], s_std[8];
+    if (threadIdx.x < C) {
+        const double mean = sums[threadIdx.x] / count;
+        const double var = fmax(sums[C + threadIdx.x] / count - mean * mean, 0.0);
+        s_mean[threadIdx.x] = static_cast<float>(mean);
+        s_std[threadIdx.x] = static_cast<float>(sqrt(var));
+    }
+    __syncthreads();
+    const int dlen = C * per_chan;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % dlen) / per_chan;
+        desc[idx] = (desc[idx] - s_mean[c]) / s_std[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// projection: proj[d, m] = sum_k desc[m, k] * dirs[k, d]     (fp32 FFMA; K = 147 is not worth
+// a tensor-core pipeline at 1e-4 parity -- see DESIGN.md "projection")
+// CTA tile: 128 rows x 64 directions, whole K resident in shared memory.
+// thread tile: 4 rows (lane + 32 i) x 8 directions (warp * 8 ..)
+// ---------------------------------------------------------------------------------------------
+constexpr int kPM = 128, kPN = 64, kPThreads = 256;
+
+__global__ void __launch_bounds__(kPThreads) project_kernel(const float* __restrict__ desc, int64_t rows, int K,
+                                                            const float* __restrict__ dirs, int D, float* __restrict__ proj) {
+    extern __shared__ __align__(16) float s_proj[];
+    const int KA = K | 1;                       // odd pitch: lane <-> row reads are conflict-free
+    float* s_a = s_proj;                        // [kPM][KA]
+    float* s_b = s_proj + kPM * KA;             // [K][kPN]
+    const int64_t m0 = static_cast<int64_t>(blockIdx.x) * kPM;
+    const int d0 = blockIdx.y * kPN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mrows = (rows - m0 < kPM) ? static_cast<int>(rows - m0) : kPM;
+
+    for (int idx = tid; idx < kPM * K; idx += kPThreads) {
+        const int r = idx / K, k = idx - r * K;
+        s_a[r * KA + k] = (r < mrows) ? __ldg(desc + (m0 + r) * K + k) : 0.0f;
+    }
+    for (int idx = tid; idx < K * kPN; idx += kPThreads) {
+        const int k = idx / kPN, d = idx - k * kPN;
+        s_b[idx] = (d0 + d < D) ? __ldg(dirs + static_cast<size_t>(k) * D + d0 + d) : 0.0f;
+    }
+    __syncthreads();
+
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    const float* a0 = s_a + lane * KA;
+    const float* b0 = s_b + warp * 8;
+#pragma unroll 7
+    for (int k = 0; k < K; ++k) {
+        float av[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = a0[i * 32 * KA + k];
+        const float4 b_lo = *reinterpret_cast<const float4*>(b0 + k * kPN);
+        const float4 b_hi = *reinterpret_cast<const float4*>(b0 + k * kPN + 4);
+        const float bv[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = d0 + warp * 8 + j;
+        if (d >= D) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            if (r < mrows) proj[static_cast<size_t>(d) * rows + m0 + r] = acc[i][j];
+        }
+    }
+}
+
+__global__ void absdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count, double* __restrict__ out) {
+    double acc = 0.0;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < count;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        acc += static_cast<double>(fabsf(__ldg(a + idx) - __ldg(b + idx)));
+    acc = warp_sum(acc);
+    __shared__ double s_part[32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? s_part[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out, v);
+    }
+}
+
+unsigned grid_for(int64_t total, int threads, int per_sm) {
+    const int64_t want = ceil_div64(total, threads);
+    const int64_t cap = static_cast<int64_t>(device_sm_count()) * per_sm;
+    return static_cast<unsigned>(std::max<int64_t>(1, std::min(want, cap)));
+}
+
+}  // namespace
+}  // namespace bgan
+
+using namespace bgan;
+
+extern "C" int bgan_pyr_down_f32(const float* x, float* y, int planes, int height, int width, void* stream) {
+    BGAN_REQUIRE(x && y && planes > 0 && height > 0 && width > 0, BGAN_E_BADARG, "bgan_pyr_down_f32: bad arguments");
+    const int oh = (height + 1) / 2, ow = (width + 1) / 2;
+    const int64_t total = static_cast<int64_t>(planes) * oh * ow;
+    pyr_down_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, planes, height, width, oh, ow);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bgan_pyr_up_f32(const float* x, const float* minuend, float* y, int planes, int h, int w, void* stream) {
+    BGAN_REQUIRE(x && y && planes > 0 && h > 0 && w > 0, BGAN_E_BADARG, "bgan_pyr_up_f32: bad arguments");
+    const int64_t total = static_cast<int64_t>(planes) * 4 * h * w;
+    pyr_up_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, minuend, y, planes, h, w);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bgan_swd_extract_f32(const float* level, int n, int c, int h, int w, const int32_t* px, const int32_t* py,
+                                    int nhoods_per_image, int nhood, float* desc_out, double* sums, void* stream) {
+    BGAN_REQUIRE(level && px && py && desc_out && sums, BGAN_E_BADARG, "bgan_swd_extract_f32: null pointer");
+    BGAN_REQUIRE(n > 0 && c > 0 && c <= 4 && nhood > 0 && (nhood & 1) && nhoods_per_image > 0 && h >= nhood && w >= nhood,
+                 BGAN_E_BADARG, "bgan_swd_extract_f32: bad shape (n=%d c=%d h=%d w=%d nhood=%d)", n, c, h, w, nhood);
+    const int64_t n_desc = static_cast<int64_t>(n) * nhoods_per_image;
+    const int64_t total = n_desc * c * nhood * nhood;
+    extract_kernel<4><<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(level, c, h, w, px, py, nhoods_per_image,
+                                                                                          nhood, n_desc, desc_out, sums);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bgan_swd_normalise_f32(float* desc, int64_t rows, int c, int per_channel, const double* sums, double count,
+                                      void* stream) {
+    BGAN_REQUIRE(desc && sums && rows > 0 && c > 0 && c <= 8 && per_channel > 0 && count > 0, BGAN_E_BADARG,
+                 "bgan_swd_normalise_f32: bad arguments");
+    const int64_t total = rows * c * per_channel;
+    normalise_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(desc, total, c, per_channel, sums, count);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bgan_swd_project_f32(const float* desc, int64_t rows, int k, const float* dirs, int d, float* proj_out, void* stream) {
+    BGAN_REQUIRE(desc && dirs && proj_out && rows > 0 && k > 0 && d > 0, BGAN_E_BADARG, "bgan_swd_project_f32: bad arguments");
+    const size_t smem = sizeof(float) * (static_cast<size_t>(kPM) * (k | 1) + static_cast<size_t>(k) * kPN);
+    BGAN_REQUIRE(smem <= 227 * 1024, BGAN_E_UNSUPPORTED, "bgan_swd_project_f32: descriptor length %d too large", k);
+    BGAN_REQUIRE(ceil_div64(rows, kPM) < (int64_t(1) << 31), BGAN_E_BADARG, "too many rows");
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    BGAN_CUDA_OK(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        BGAN_CUDA_OK(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_dev = dev;
+    }
+    dim3 grid(static_cast<unsigned>(ceil_div64(rows, kPM)), static_cast<unsigned>(ceil_div(d, kPN)));
+    project_kernel<<<grid, kPThreads, smem, static_cast<cudaStream_t>(stream)>>>(desc, rows, k, dirs, d, proj_out);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bgan_swd_absdiff_sum_f32(const float* a, const float* b, int64_t count, double* sum_out, void* stream) {
+    BGAN_REQUIRE(a && b && sum_out && count > 0, BGAN_E_BADARG, "bgan_swd_absdiff_sum_f32: bad arguments");
+    absdiff_sum_kernel<<<grid_for(count, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, count, sum_out);
+    BGAN_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,240 @@
+"""PyTorch custom ops over the C ABI (include/bgan.h).  PyTorch is plumbing here: device memory,
+the current stream and autograd bookkeeping; every FLOP runs in libbgan_b200.so.
+
+``bgan::blur2d`` is differentiable to any order: the blur matrix is symmetric (zero "same" padding
+applied after tap normalisation), so the vector-Jacobian product of the op is the op
+itself applied to the incoming gradient.  That covers the 7 blur applications of one WGAN-GP step
+(reference wgan.py:136-140,163-166,234-246): 4 forward, 2 backward, 1 double-backward.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_NCHW, LAYOUT_NHWC, RULE_EXPLICIT, RULE_TF, RULE_TORCH  # noqa: F401
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            "%s: expected a CUDA tensor, got device %s. blurred_gan_b200 has no CPU path "
+            "(the CPU restatement lives in oracle/ and is test infrastructure only)." % (what, t.device)
+        )
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s: expected float32, got %s" % (what, t.dtype))
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------------------------
+# blur
+# --------------------------------------------------------------------------------------------
+def _dims(x: torch.Tensor, layout: int) -> tuple[int, int, int, int]:
+    if x.dim() != 4:
+        raise RuntimeError("blur2d: expected a 4-D tensor, got shape %s" % (tuple(x.shape),))
+    if layout == LAYOUT_NCHW:
+        n, c, h, w = x.shape
+    else:
+        n, h, w, c = x.shape
+    return n, c, h, w
+
+
+@torch.library.custom_op("bgan::blur2d", mutates_args=(), device_types="cuda")
+def blur2d(x: torch.Tensor, layout: int, rule: int, std_eff: float, radius: int) -> torch.Tensor:
+    """y = B x with taps generated in-kernel from (rule, std_eff, radius)."""
+    _require_cuda(x, "blur2d")
+    lib = _lib.load()
+    x = x.contiguous()
+    n, c, h, w = _dims(x, layout)
+    y = torch.empty_like(x)
+    if x.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.bgan_blur2d_workspace_bytes(n, c, h, w, layout, radius)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        rc = lib.bgan_blur2d_f32(x.data_ptr(), y.data_ptr(), n, c, h, w, layout, rule, float(std_eff), radius, None,
+                                 ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr())
+    _lib.check(rc, "bgan_blur2d_f32")
+    return y
+
+
+@blur2d.register_fake
+def _(x, layout, rule, std_eff, radius):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def _blur2d_backward(ctx, grad):
+    return blur2d(grad, ctx.layout, ctx.rule, ctx.std_eff, ctx.radius), None, None, None, None
+
+
+def _blur2d_setup(ctx, inputs, output):
+    _, ctx.layout, ctx.rule, ctx.std_eff, ctx.radius = inputs
+
+
+blur2d.register_autograd(_blur2d_backward, setup_context=_blur2d_setup)
+
+
+@torch.library.custom_op("bgan::blur2d_taps", mutates_args=(), device_types="cuda")
+def blur2d_taps(x: torch.Tensor, taps: torch.Tensor, layout: int) -> torch.Tensor:
+    """y = B x with caller-supplied taps (1-D, odd length, used as given -- not renormalised)."""
+    _require_cuda(x, "blur2d_taps")
+    _require_cuda(taps, "blur2d_taps(taps)")
+    if taps.dim() != 1 or taps.numel() % 2 != 1:
+        raise RuntimeError("blur2d_taps: taps must be 1-D with odd length")
+    lib = _lib.load()
+    x = x.contiguous()
+    taps = taps.contiguous()
+    n, c, h, w = _dims(x, layout)
+    radius = taps.numel() // 2
+    y = torch.empty_like(x)
+    if x.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.bgan_blur2d_workspace_bytes(n, c, h, w, layout, radius)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        rc = lib.bgan_blur2d_f32(x.data_ptr(), y.data_ptr(), n, c, h, w, layout, RULE_EXPLICIT, 1.0, radius, taps.data_ptr(),
+                                 ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr())
+    _lib.check(rc, "bgan_blur2d_f32")
+    return y
+
+
+@blur2d_taps.register_fake
+def _(x, taps, layout):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def _blur2d_taps_backward(ctx, grad):
+    (taps,) = ctx.saved_tensors
+    # correlation with taps t is adjoint to correlation with reversed taps; symmetric taps are their own reverse
+    return blur2d_taps(grad, torch.flip(taps, dims=(0,)), ctx.layout), None, None
+
+
+def _blur2d_taps_setup(ctx, inputs, output):
+    _, taps, ctx.layout = inputs
+    ctx.save_for_backward(taps)
+
+
+blur2d_taps.register_autograd(_blur2d_taps_backward, setup_context=_blur2d_taps_setup)
+
+
+def device_taps(rule: int, std_eff: float, radius: int, device) -> torch.Tensor:
+    """The 2*radius+1 taps exactly as the blur kernels compute them (for parity tests / `.kernel`)."""
+    lib = _lib.load()
+    out = torch.empty(2 * radius + 1, dtype=torch.float32, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.bgan_blur_taps_f32(rule, float(std_eff), radius, out.data_ptr(), _stream_ptr()), "bgan_blur_taps_f32")
+    return out
+
+
+def last_blur_path() -> int:
+    return _lib.load().bgan_blur2d_last_path()
+
+
+# --------------------------------------------------------------------------------------------
+# SWD building blocks (no autograd: the metric is evaluation-only, reference callbacks.py:153-179)
+# --------------------------------------------------------------------------------------------
+def pyr_down(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x, "pyr_down")
+    assert x.dim() == 4
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, (h + 1) // 2, (w + 1) // 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().bgan_pyr_down_f32(x.data_ptr(), y.data_ptr(), n * c, h, w, _stream_ptr()), "bgan_pyr_down_f32")
+    return y
+
+
+def pyr_up(x: torch.Tensor, minuend: torch.Tensor | None = None) -> torch.Tensor:
+    """pyr_up(x), or ``minuend - pyr_up(x)`` fused when ``minuend`` is given."""
+    _require_cuda(x, "pyr_up")
+    assert x.dim() == 4
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    mptr = None
+    if minuend is not None:
+        _require_cuda(minuend, "pyr_up(minuend)")
+        assert tuple(minuend.shape) == tuple(y.shape)
+        minuend = minuend.contiguous()
+        mptr = minuend.data_ptr()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().bgan_pyr_up_f32(x.data_ptr(), mptr, y.data_ptr(), n * c, h, w, _stream_ptr()), "bgan_pyr_up_f32")
+    return y
+
+
+def swd_extract(level: torch.Tensor, px, py, nhoods_per_image: int, nhood: int, sums: torch.Tensor) -> torch.Tensor:
+    """Gather descriptors [n*per_image, C, nhood, nhood] and accumulate channel statistics into ``sums`` (fp64 [2C])."""
+    _require_cuda(level, "swd_extract")
+    level = level.contiguous()
+    n, c, h, w = level.shape
+    dev = level.device
+    px_t = torch.as_tensor(np.ascontiguousarray(px, dtype=np.int32)).to(dev) if not torch.is_tensor(px) else px.to(dev, torch.int32)
+    py_t = torch.as_tensor(np.ascontiguousarray(py, dtype=np.int32)).to(dev) if not torch.is_tensor(py) else py.to(dev, torch.int32)
+    assert px_t.numel() == n * nhoods_per_image and py_t.numel() == n * nhoods_per_image
+    assert sums.dtype == torch.float64 and sums.numel() == 2 * c and sums.is_cuda
+    out = torch.empty((n * nhoods_per_image, c, nhood, nhood), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().bgan_swd_extract_f32(level.data_ptr(), n, c, h, w, px_t.data_ptr(), py_t.data_ptr(), nhoods_per_image,
+                                              nhood, out.data_ptr(), sums.data_ptr(), _stream_ptr())
+    _lib.check(rc, "bgan_swd_extract_f32")
+    return out
+
+
+def swd_normalise_(desc: torch.Tensor, sums: torch.Tensor, count: float) -> torch.Tensor:
+    """In place (desc - mean_c) / std_c for desc [rows, C, a, b]; mean/std derived on device from ``sums``."""
+    _require_cuda(desc, "swd_normalise_")
+    assert desc.is_contiguous() and desc.dim() == 4
+    rows, c, a, b = desc.shape
+    with torch.cuda.device(desc.device):
+        rc = _lib.load().bgan_swd_normalise_f32(desc.data_ptr(), rows, c, a * b, sums.data_ptr(), float(count), _stream_ptr())
+    _lib.check(rc, "bgan_swd_normalise_f32")
+    return desc
+
+
+def swd_project(desc: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
+    """desc [rows, k] @ dirs [k, d] -> direction-major [d, rows]."""
+    _require_cuda(desc, "swd_project")
+    _require_cuda(dirs, "swd_project(dirs)")
+    desc = desc.contiguous()
+    dirs = dirs.contiguous()
+    rows, k = desc.shape
+    assert dirs.shape[0] == k
+    d = dirs.shape[1]
+    out = torch.empty((d, rows), dtype=torch.float32, device=desc.device)
+    with torch.cuda.device(desc.device):
+        rc = _lib.load().bgan_swd_project_f32(desc.data_ptr(), rows, k, dirs.data_ptr(), d, out.data_ptr(), _stream_ptr())
+    _lib.check(rc, "bgan_swd_project_f32")
+    return out
+
+
+def swd_sort_(keys: torch.Tensor) -> torch.Tensor:
+    """Ascending in-place sort of every row of keys [segments, rows]."""
+    _require_cuda(keys, "swd_sort_")
+    assert keys.is_contiguous() and keys.dim() == 2
+    segments, rows = keys.shape
+    lib = _lib.load()
+    with torch.cuda.device(keys.device):
+        done = 0
+        while done < segments:  # the kernel grid caps segments per launch
+            seg = min(segments - done, 32768)
+            ws_bytes = lib.bgan_swd_sort_workspace_bytes(rows, seg)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+            part = keys[done : done + seg]
+            _lib.check(lib.bgan_swd_sort_f32(part.data_ptr(), rows, seg, ws.data_ptr(), ws_bytes, _stream_ptr()), "bgan_swd_sort_f32")
+            done += seg
+    return keys
+
+
+def swd_absdiff_sum(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """sum |a - b| as a 1-element fp64 device tensor."""
+    _require_cuda(a, "swd_absdiff_sum")
+    _require_cuda(b, "swd_absdiff_sum")
+    assert a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    out = torch.zeros(1, dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().bgan_swd_absdiff_sum_f32(a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream_ptr())
+    _lib.check(rc, "bgan_swd_absdiff_sum_f32")
+    return out

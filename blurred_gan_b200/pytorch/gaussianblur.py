@@ -1,0 +1,96 @@
+"""Drop-in for the reference's ``pytorch/gaussianblur.py`` (lines 9-71), minus its script tail.
+
+Same names, same arguments, same results -- including the reference's quirks, which parity is
+defined against:
+
+* the Gaussian normaliser sits inside the exponential (``pytorch/gaussianblur.py:11``);
+* ``kernel_size`` is ``max(3, odd_up(ceil(5 std)))`` clipped to ``odd_up(min(H, W)) - 2`` (``:17-30,43-57``),
+  and the clip uses the image size remembered from the *previous* forward until the next one (``:37,61``);
+* zero "same" padding after normalisation, horizontal pass then vertical pass (``:67-70``).
+
+Extensions over the reference (which is single-channel and CPU-only): any number of
+channels (depthwise, same taps), CUDA tensors, autograd to any order.  ``forward`` runs the fused
+sm_100a kernel; there is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def gaussian_kernel_1d(std, kernel_size: int) -> torch.Tensor:
+    """Taps of the reference, shape [1, kernel_size], fp32 (``pytorch/gaussianblur.py:9-14``).
+
+    Host-side helper kept for API parity (``GaussianBlur.kernel``); the blur kernels generate the
+    same taps on the device.
+    """
+    std_t = torch.as_tensor(std, dtype=torch.float32).detach().reshape(-1)[:1].cpu()
+    half = kernel_size // 2
+    offsets = torch.arange(-half, half + 1, dtype=torch.float32).unsqueeze(0)
+    exponent = (offsets.square() / (2 * std_t.square())) / (math.sqrt(2 * math.pi) * std_t)
+    g = torch.exp(-exponent)
+    return g / g.sum()
+
+
+def nearest_odd_integer(number, higher: bool = True) -> int:
+    """``pytorch/gaussianblur.py:17-20``."""
+    integer = int(np.ceil(float(number)))
+    odd = integer if integer % 2 == 1 else integer + 1
+    return odd if higher else odd - 2
+
+
+def appropriate_kernel_size(std) -> int:
+    """``pytorch/gaussianblur.py:23-30``: nearest odd integer above 5 std (fp32 product), at least 3."""
+    five_std = float(np.float32(5.0) * np.float32(float(std)))
+    return max(nearest_odd_integer(five_std), 3)
+
+
+class GaussianBlur(nn.Module):
+    def __init__(self, std: float = 2.0):
+        super().__init__()
+        # frozen Parameter named `std`, shape [1]: part of state_dict, assigned by the sigma controllers
+        self.std = nn.Parameter(torch.Tensor([std]), requires_grad=False)
+        self._image_size = None
+        self._std_cache = (None, None, float(std))  # (version, data_ptr, host value)
+
+    # -- host shadow of std: one device->host read per *change* of the Parameter, not per forward ---------
+    def std_value(self) -> float:
+        p = self.std
+        key = (p._version, p.data_ptr())
+        if (self._std_cache[0], self._std_cache[1]) != key:
+            self._std_cache = (key[0], key[1], float(p.detach().reshape(-1)[0].item()))
+        return self._std_cache[2]
+
+    def set_std(self, value: float) -> None:
+        """Assign a new std without a device->host synchronisation (what a sigma controller should call)."""
+        with torch.no_grad():
+            self.std.fill_(float(value))
+        self._std_cache = (self.std._version, self.std.data_ptr(), float(np.float32(value)))
+
+    @property
+    def kernel(self) -> torch.Tensor:
+        return gaussian_kernel_1d(std=self.std_value(), kernel_size=self.kernel_size).to(self.std.device)
+
+    @property
+    def kernel_size(self) -> int:
+        k_size = appropriate_kernel_size(self.std_value())
+        if self._image_size:
+            k_size = min(k_size, nearest_odd_integer(self._image_size, higher=False))
+        assert k_size % 2 == 1, "kernel size should be odd"
+        return k_size
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        if inputs.dim() != 4:
+            raise RuntimeError("GaussianBlur expects [N, C, H, W], got %s" % (tuple(inputs.shape),))
+        if not inputs.is_cuda:
+            raise RuntimeError("GaussianBlur (blurred_gan_b200) runs on CUDA tensors only; there is no CPU fallback")
+        self._image_size = min(inputs.shape[-2:])
+        k = self.kernel_size
+        if k < 1:
+            raise AssertionError("kernel size should be odd")
+        return ops.blur2d(inputs, ops.LAYOUT_NCHW, ops.RULE_TORCH, self.std_value(), k // 2)

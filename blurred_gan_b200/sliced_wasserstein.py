@@ -1,0 +1,197 @@
+"""Drop-in for the reference's ``sliced_wasserstein.py`` with every array operation on the GPU.
+
+Same names and positional signatures as the reference; arrays may be numpy (as in the reference) or
+torch tensors, results of the free functions are CUDA ``torch.Tensor`` and ``API.end`` returns a
+list of Python floats like the reference.  What stays on the host is only what parity pins there:
+the random draws.  Patch positions and projection directions come from numpy's *global* legacy
+RandomState in exactly the reference's order -- ``randint`` x then y per level per
+``feed``, 4x ``randn(147, 128)`` per level per ``end`` (also in ``end('reals')``, where the
+reference draws them and gets 0) -- so that identical seeds give identical patches and projections.
+
+Deliberate differences: inputs are never mutated (the reference overwrites float32 inputs);
+the real-vs-real distance of ``end('reals')`` is returned as the exact 0 the reference computes,
+without sorting anything.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+# ----------------------------------------------------------------------------
+
+
+def _to_device(a, device=None) -> torch.Tensor:
+    if torch.is_tensor(a):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if device is None:
+        device = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def get_descriptors_for_minibatch(minibatch, nhood_size, nhoods_per_image, sums=None):
+    """``sliced_wasserstein.py:13-23``.  Returns [n * nhoods_per_image, 3, nhood, nhood] on the GPU;
+    if ``sums`` (fp64 [6] CUDA tensor) is given, per-channel sum / sum of squares are accumulated into it."""
+    mb = _to_device(minibatch)
+    S = mb.shape  # (minibatch, channel, height, width)
+    assert len(S) == 4 and S[1] == 3
+    N = nhoods_per_image * S[0]
+    H = nhood_size // 2
+    # same two draws, same order and shapes as the reference: columns first, then rows
+    x = np.random.randint(H, S[3] - H, size=(N, 1, 1, 1))
+    y = np.random.randint(H, S[2] - H, size=(N, 1, 1, 1))
+    if sums is None:
+        sums = torch.zeros(2 * S[1], dtype=torch.float64, device=mb.device)
+    return ops.swd_extract(mb, x.reshape(-1), y.reshape(-1), nhoods_per_image, nhood_size, sums)
+
+
+# ----------------------------------------------------------------------------
+
+
+def finalize_descriptors(desc, sums=None):
+    """``sliced_wasserstein.py:27-34``: concatenate, standardise each channel over (descriptor, i, j)
+    with the population std, flatten to [rows, C * nhood * nhood]."""
+    if isinstance(desc, list):
+        desc = torch.cat([_to_device(d) for d in desc], dim=0)
+    else:
+        desc = _to_device(desc).clone()
+    assert desc.dim() == 4  # (neighborhood, channel, height, width)
+    rows, c, a, b = desc.shape
+    if sums is None:
+        d64 = desc.to(torch.float64)
+        sums = torch.cat([d64.sum(dim=(0, 2, 3)), d64.square().sum(dim=(0, 2, 3))])
+    ops.swd_normalise_(desc, sums, float(rows) * a * b)
+    return desc.reshape(rows, -1)
+
+
+# ----------------------------------------------------------------------------
+
+
+def _draw_directions(dim, dirs_per_repeat):
+    dirs = np.random.randn(dim, dirs_per_repeat)  # (descriptor_component, direction)
+    dirs /= np.sqrt(np.sum(np.square(dirs), axis=0, keepdims=True))
+    return dirs.astype(np.float32)
+
+
+def sliced_wasserstein(A, B, dir_repeats, dirs_per_repeat):
+    """``sliced_wasserstein.py:38-51``: mean over repeats of mean |sort(A dirs) - sort(B dirs)|."""
+    A = _to_device(A)
+    B = _to_device(B, A.device)
+    assert A.dim() == 2 and A.shape == B.shape  # (neighborhood, descriptor_component)
+    rows, dim = A.shape
+    dirs = np.concatenate([_draw_directions(dim, dirs_per_repeat) for _ in range(dir_repeats)], axis=1)
+    dirs_t = torch.from_numpy(dirs).to(A.device)
+    projA = ops.swd_sort_(ops.swd_project(A, dirs_t))  # [repeats * dirs, rows], each row sorted
+    projB = ops.swd_sort_(ops.swd_project(B, dirs_t))
+    sums = torch.cat([
+        ops.swd_absdiff_sum(projA[r * dirs_per_repeat : (r + 1) * dirs_per_repeat], projB[r * dirs_per_repeat : (r + 1) * dirs_per_repeat])
+        for r in range(dir_repeats)
+    ])
+    per_repeat = (sums / float(rows * dirs_per_repeat)).to(torch.float32)  # np.mean(dists) is fp32 in the reference
+    return np.float32(per_repeat.to(torch.float64).mean().item())
+
+
+# ----------------------------------------------------------------------------
+
+
+def downscale_minibatch(minibatch, lod):
+    """``sliced_wasserstein.py:55-61`` (not used by ``API``; plain torch, kept for surface parity)."""
+    if lod == 0:
+        return minibatch
+    t = _to_device(minibatch)
+    for _ in range(lod):
+        t = (t[:, :, 0::2, 0::2] + t[:, :, 0::2, 1::2] + t[:, :, 1::2, 0::2] + t[:, :, 1::2, 1::2]) * 0.25
+    return torch.round(t).clip(0, 255).to(torch.uint8)
+
+
+# ----------------------------------------------------------------------------
+
+_binomial5 = np.float32([1, 4, 6, 4, 1])
+gaussian_filter = np.outer(_binomial5, _binomial5).astype(np.float32) / 256.0  # same 5x5 table as the reference's :65-70
+
+
+def pyr_down(minibatch):  # matches cv2.pyrDown()
+    mb = _to_device(minibatch)
+    assert mb.dim() == 4
+    return ops.pyr_down(mb)
+
+
+def pyr_up(minibatch):  # matches cv2.pyrUp()
+    mb = _to_device(minibatch)
+    assert mb.dim() == 4
+    return ops.pyr_up(mb)
+
+
+def generate_laplacian_pyramid(minibatch, num_levels):
+    """``sliced_wasserstein.py:83-88``; the residual ``g - pyr_up(pyr_down(g))`` is one fused kernel."""
+    pyramid = [_to_device(minibatch)]
+    for _ in range(1, num_levels):
+        coarse = ops.pyr_down(pyramid[-1])
+        pyramid[-1] = ops.pyr_up(coarse, minuend=pyramid[-1])
+        pyramid.append(coarse)
+    return pyramid
+
+
+def reconstruct_laplacian_pyramid(pyramid):
+    minibatch = _to_device(pyramid[-1])
+    for level in pyramid[-2::-1]:
+        minibatch = ops.pyr_up(minibatch) + _to_device(level, minibatch.device)
+    return minibatch
+
+
+# ----------------------------------------------------------------------------
+
+
+class API:
+    """``sliced_wasserstein.py:98-133``: begin / feed / end state machine over a Laplacian pyramid."""
+
+    def __init__(self, image_shape, device=None):
+        self.nhood_size, self.nhoods_per_image = 7, 128
+        self.dir_repeats, self.dirs_per_repeat = 4, 128
+        self.device = device
+        # one pyramid level per power of two down to 16 px (image_shape = (C, H, W); H drives it, like the reference)
+        self.resolutions = []
+        size = image_shape[1]
+        while size >= 16:
+            self.resolutions.append(size)
+            size //= 2
+
+    def get_metric_names(self):
+        return [f"SWDx1e3_{res}" for res in self.resolutions] + ["SWDx1e3_avg"]
+
+    def get_metric_formatting(self):
+        return ["%-13.4f"] * (len(self.resolutions) + 1)
+
+    def begin(self, mode):
+        assert mode in ['warmup', 'reals', 'fakes']
+        self.descriptors = [[] for _ in self.resolutions]
+        self._sums = None  # per level: fp64 [sum_c..., sumsq_c...] accumulated on the device by the gather kernel
+
+    def feed(self, mode, minibatch):
+        mb = _to_device(minibatch, self.device)
+        levels = generate_laplacian_pyramid(mb, len(self.resolutions))
+        if self._sums is None:
+            self._sums = [torch.zeros(2 * mb.shape[1], dtype=torch.float64, device=mb.device) for _ in levels]
+        for lod, level in enumerate(levels):  # level order fixes the RNG order: x then y, finest level first
+            self.descriptors[lod].append(
+                get_descriptors_for_minibatch(level, self.nhood_size, self.nhoods_per_image, self._sums[lod]))
+
+    def end(self, mode):
+        desc = [finalize_descriptors(d, s) for d, s in zip(self.descriptors, self._sums)]
+        del self.descriptors
+        if mode in ['warmup', 'reals']:
+            self.desc_real = desc
+            # The reference evaluates sliced_wasserstein(real, real) here: dir_repeats randn draws per level and
+            # a result of exactly 0.  Consume the draws (they position the stream for the fakes), skip the sorts.
+            for d in desc:
+                for _ in range(self.dir_repeats):
+                    np.random.randn(d.shape[1], self.dirs_per_repeat)
+            dist = [np.float32(0.0)] * len(desc)
+        else:
+            dist = [sliced_wasserstein(real, fake, self.dir_repeats, self.dirs_per_repeat)
+                    for real, fake in zip(self.desc_real, desc)]
+        scaled = [d * 1e3 for d in dist]
+        return scaled + [np.mean(scaled)]

@@ -1,0 +1,127 @@
+/*
+ * bgan.h -- C ABI of libbgan_b200.so: the sm_100a kernels behind blurred-GAN's hot path
+ * (sigma-annealed Gaussian blur fwd/bwd + sliced-Wasserstein evaluation).
+ *
+ * The reference (lebrice/blurred-GAN) has no FFI of its own: its boundary is the Python
+ * surface of three files.  Each entry point below names the reference lines whose
+ * arithmetic it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every pointer called "device" is a raw CUDA device pointer owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t. the host;
+ *   - no call allocates persistent device memory: scratch is passed in (`ws`, `ws_bytes`),
+ *     sized by the matching *_workspace_bytes query;
+ *   - return value: 0 = OK, > 0 = cudaError_t, < 0 = argument error (BGAN_E_*);
+ *     bgan_last_error() returns a thread-local message for the last non-zero return;
+ *   - functions are re-entrant across streams and devices (the current device must be
+ *     the device that owns the pointers).
+ */
+#ifndef BGAN_H_
+#define BGAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGAN_ABI_VERSION 1
+
+/* tap rules */
+#define BGAN_RULE_TORCH 0    /* pytorch/gaussianblur.py:9-14 (normaliser inside the exp)  */
+#define BGAN_RULE_TF 1       /* gaussian_blur.py:83-88 (true Gaussian)                   */
+#define BGAN_RULE_EXPLICIT 2 /* caller supplies 2*radius+1 taps on the device             */
+
+/* memory layouts */
+#define BGAN_LAYOUT_NCHW 0
+#define BGAN_LAYOUT_NHWC 1
+
+/* argument errors */
+#define BGAN_E_BADARG (-1)
+#define BGAN_E_WORKSPACE (-2)
+#define BGAN_E_UNSUPPORTED (-3)
+
+int bgan_version(void);
+const char* bgan_last_error(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Gaussian blur                                                                          */
+/* ------------------------------------------------------------------------------------ */
+
+/* Host-only.  Kernel-size rules:
+ *   BGAN_RULE_TORCH: pytorch/gaussianblur.py:17-30,43-57,61  k = max(3, odd_up(ceil(5 std))),
+ *                    clipped to odd_up(min(H,W)) - 2;            std_eff = std
+ *   BGAN_RULE_TF:    gaussian_blur.py:21-31,58-59,65-72          k = floor(6 std) + 1, clipped
+ *                    to [3, max(H,W)];  std_eff = max((k-1)/6, 0.01); taps span [-(k/2), k/2]
+ * Outputs: *kernel_size = k, *radius = k / 2, *std_eff = the std that enters the exponential. */
+int bgan_blur_plan(int rule, float std, int height, int width, int* kernel_size, int* radius, float* std_eff);
+
+/* Writes the 2*radius+1 normalised taps exactly as the blur kernels compute them
+ * (pytorch/gaussianblur.py:9-14 / gaussian_blur.py:83-88) to device memory. */
+int bgan_blur_taps_f32(int rule, float std_eff, int radius, float* taps_out_device, void* stream);
+
+/* Scratch needed by bgan_blur2d_f32 for this problem (0 when the fused single-kernel path applies). */
+size_t bgan_blur2d_workspace_bytes(int n, int c, int height, int width, int layout, int radius);
+
+/* y = B x: separable depthwise blur, zero "same" padding, taps generated in-kernel from
+ * (rule, std_eff, radius) or read from taps_device (rule == BGAN_RULE_EXPLICIT).
+ * Replaces GaussianBlur.forward (pytorch/gaussianblur.py:59-71), gaussian_blur()
+ * (gaussian_blur.py:91-132) and -- B being self-adjoint -- their autograd backward and
+ * double-backward (call sites wgan.py:140,166,244): backward is the same call on grad_output.
+ * x and y are device pointers to N*C*H*W floats in `layout`; x == y is NOT allowed. */
+int bgan_blur2d_f32(const float* x_device, float* y_device, int n, int c, int height, int width, int layout,
+                    int rule, float std_eff, int radius, const float* taps_device,
+                    void* ws_device, size_t ws_bytes, void* stream);
+
+/* How the last bgan_blur2d_f32 call on this thread was executed: 1 = fused tile kernel with TMA
+ * staging, 2 = fused tile kernel with plain loads, 3 = two launches (row pass, column pass). */
+int bgan_blur2d_last_path(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Sliced Wasserstein distance (sliced_wasserstein.py)                                    */
+/* ------------------------------------------------------------------------------------ */
+
+/* sliced_wasserstein.py:72-74  pyr_down: 5x5 binomial/256, mirror border, keep even rows/cols.
+ * x: [planes, H, W] -> y: [planes, (H+1)/2, (W+1)/2].  fp64 accumulate, fp32 store. */
+int bgan_pyr_down_f32(const float* x_device, float* y_device, int planes, int height, int width, void* stream);
+
+/* sliced_wasserstein.py:76-81  pyr_up: zero-stuff to 2x, 5x5 binomial * 4/256, mirror border.
+ * x: [planes, h, w] -> y: [planes, 2h, 2w].  If minuend_device != NULL writes
+ * y = minuend - pyr_up(x) instead (the Laplacian residual of :87). */
+int bgan_pyr_up_f32(const float* x_device, const float* minuend_device, float* y_device, int planes, int h, int w,
+                    void* stream);
+
+/* sliced_wasserstein.py:13-23  gather nhoods_per_image patches of nhood x nhood x C per image at
+ * the caller-drawn centres (px = column, py = row; int32 device arrays of n*nhoods_per_image)
+ * into desc_out[m, c, i, j] = level[m / per_image, c, py[m]+j-half, px[m]+i-half], and add the
+ * per-channel sum and sum of squares of everything written to sums_device[0..C) / [C..2C)
+ * (fp64, caller zeroes them) -- the statistics half of finalize_descriptors (:31-32). */
+int bgan_swd_extract_f32(const float* level_device, int n, int c, int h, int w, const int32_t* px_device,
+                         const int32_t* py_device, int nhoods_per_image, int nhood, float* desc_out_device,
+                         double* sums_device, void* stream);
+
+/* sliced_wasserstein.py:31-32  desc = (desc - mean_c) / std_c in place, with mean/std derived on
+ * the device from sums_device (as filled by bgan_swd_extract_f32, possibly all-reduced across
+ * ranks) and `count` = number of values per channel.  rows x (C*per_channel) floats. */
+int bgan_swd_normalise_f32(float* desc_device, int64_t rows, int c, int per_channel, const double* sums_device,
+                           double count, void* stream);
+
+/* sliced_wasserstein.py:45-46  proj = desc @ dirs, written direction-major:
+ * desc [rows, k] row-major, dirs [k, d] row-major -> proj_out [d, rows]. */
+int bgan_swd_project_f32(const float* desc_device, int64_t rows, int k, const float* dirs_device, int d,
+                         float* proj_out_device, void* stream);
+
+/* sliced_wasserstein.py:47-48  ascending sort of each of the `segments` contiguous runs of `rows`
+ * floats, in place (LSD radix sort; ws from the query below). */
+size_t bgan_swd_sort_workspace_bytes(int64_t rows, int segments);
+int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws_device, size_t ws_bytes, void* stream);
+
+/* sliced_wasserstein.py:49-50  *sum_out_device += sum_i |a[i] - b[i]| (fp64; caller zeroes it). */
+int bgan_swd_absdiff_sum_f32(const float* a_device, const float* b_device, int64_t count, double* sum_out_device,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGAN_H_ */
