@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Benchmark of the blurred-GAN hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Workload (BASELINE.json configs[1]): GaussianBlur forward + backward on a synthetic CelebA-128 batch,
+256 x 3 x 128 x 128 fp32 NCHW, torch tap rule, std swept over {0.5, 1, 2, 3, 5, 8, 12, 16, 23}.
+One *step* = one forward blur (of x) plus one backward blur (of grad_y -- the operator is self-adjoint,
+so backward is the same kernel) at every std of the sweep: 18 kernel launches, 9 x 256 images.
+
+  value  images/s, whole job, inputs resident in HBM, CUDA-graph replay of the step's launches through the C ABI,
+         timed with CUDA events; buffer sets are rotated so that consecutive steps never re-touch L2-resident data.
+  e2e    the same metric through the public module (GaussianBlur(std)(x); y.backward(g)) with HOST buffers:
+         pinned host -> device copies of x and grad_y and device -> host copies of y and grad_x inside the timed region.
+  roofline      achieved = algorithmic bytes of one launch (read N*C*H*W*4, write N*C*H*W*4) / mean launch time.
+  cpu_baseline  the oracle port of the reference's own CPU path (two F.conv2d calls + ATen autograd), all host threads,
+                on a bounded sample of the same workload.
+  swd    secondary: sliced_wasserstein.API evaluation time on synthetic 128x128x3 images (BASELINE configs[4] shape).
+
+`--impl reference` times only the CPU port and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STD_SWEEP = [0.5, 1.0, 2.0, 3.0, 5.0, 8.0, 12.0, 16.0, 23.0]
+BATCH, CH, H, W = 256, 3, 128, 128
+WORKLOAD = "cfg2: GaussianBlur fwd+bwd, 256x3x128x128 fp32 NCHW, torch tap rule, std sweep 0.5-23 (9 values)"
+METRIC = "GaussianBlur fwd+bwd images/s at 128x128x3"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--no-swd", action="store_true", help="skip the secondary SWD timing")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--swd-images", type=int, default=4096, help="images per set for the secondary SWD timing")
+    p.add_argument("--stds", type=str, default="", help="comma-separated override of the std sweep (profiling runs)")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port of the reference (baseline + reference arm)
+# ------------------------------------------------------------------------------------------------
+def cpu_fwd_bwd(x, g, std):
+    """Reference path on the host: forward = two F.conv2d, backward = ATen autograd of them
+    (reference pytorch/gaussianblur.py:63-70; oracle/blur_oracle.py::blur_conv2d_port)."""
+    from oracle.blur_oracle import blur_conv2d_port
+
+    xr = x.detach().requires_grad_(True)
+    y = blur_conv2d_port(xr, std)
+    y.backward(g)
+    return y, xr.grad
+
+
+def cpu_sweep_time(n_images, stds, repeats=1):
+    import torch
+
+    torch.manual_seed(0)
+    x = torch.rand(n_images, CH, H, W) * 2 - 1
+    torch.manual_seed(1)
+    g = torch.rand(n_images, CH, H, W) * 2 - 1
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for std in stds:
+            cpu_fwd_bwd(x, g, std)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_baseline(stds, budget_s=20.0):
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe_n = 8
+    cpu_sweep_time(probe_n, stds[:1])  # thread-pool / oneDNN warm-up
+    t_probe = cpu_sweep_time(probe_n, stds)
+    n = int(max(8, min(BATCH, probe_n * budget_s / max(t_probe, 1e-6))))
+    n -= n % 8
+    t = cpu_sweep_time(n, stds)
+    return {"value": n * len(stds) / t, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "%d images x %d stds of the sweep, fwd+bwd, torch %s CPU, %d threads, %.1f s" % (n, len(stds), torch.__version__, cores, t)}
+
+
+def run_reference_arm(args, stds):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    probe_n = 8
+    cpu_sweep_time(probe_n, stds[:1])
+    t_probe = cpu_sweep_time(probe_n, stds)
+    total_steps = args.steps + args.warmup
+    budget_per_step = 150.0 / max(total_steps, 1)
+    n = int(max(8, min(BATCH, probe_n * budget_per_step / max(t_probe, 1e-6))))
+    n -= n % 8
+    for _ in range(args.warmup):
+        cpu_sweep_time(n, stds)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sweep_time(n, stds)
+    dt = time.perf_counter() - t0
+    value = args.steps * n * len(stds) / dt
+    sample = "%d images x %d stds per step (bounded sample of the 256-image batch), fwd+bwd, torch %s CPU, %d threads" % (
+        n, len(stds), torch.__version__, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "stds": stds, "sample_images_per_step": n, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args, stds):
+    import torch
+    import torch.distributed as dist
+
+    from blurred_gan_b200 import _lib, ops
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    hbm_peak, peak_src = peaks()
+
+    # ---- buffers: enough rotating sets that a step never finds its data in the 126 MB L2 -------------
+    n_sets = 5
+    plane_bytes = BATCH * CH * H * W * 4
+    torch.manual_seed(1000 + rank)
+    sets = []
+    for _ in range(n_sets):
+        x = torch.rand(BATCH, CH, H, W, device=dev) * 2 - 1
+        gy = torch.rand(BATCH, CH, H, W, device=dev) * 2 - 1
+        sets.append((x, torch.empty_like(x), gy, torch.empty_like(x)))
+    plans = [_lib.blur_plan(_lib.RULE_TORCH, s, H, W) for s in stds]  # (k, radius, std_eff)
+    stream = torch.cuda.Stream(device=dev)
+
+    def launch_pair(bufs, plan):
+        x, y, gy, gx = bufs
+        _, radius, std_eff = plan
+        sp = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.bgan_blur2d_f32(x.data_ptr(), y.data_ptr(), BATCH, CH, H, W, 0, _lib.RULE_TORCH, std_eff, radius, None, None, 0, sp), "fwd")
+        _lib.check(lib.bgan_blur2d_f32(gy.data_ptr(), gx.data_ptr(), BATCH, CH, H, W, 0, _lib.RULE_TORCH, std_eff, radius, None, None, 0, sp), "bwd")
+
+    # one CUDA graph per (buffer set, std): 2 launches each, replayed from the host with no Python in between
+    with torch.cuda.stream(stream):
+        for bufs in sets[:1]:
+            for plan in plans:
+                launch_pair(bufs, plan)  # warm the attribute / occupancy caches outside capture
+    stream.synchronize()
+    graphs = []
+    for bufs in sets:
+        row = []
+        for plan in plans:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                launch_pair(bufs, plan)
+            row.append(g)
+        graphs.append(row)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up, then K timed steps ----------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            for g in graphs[i % n_sets]:
+                g.replay()
+    barrier()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in stds] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(args.steps):
+                row = graphs[(args.warmup + i) % n_sets]
+                for j, g in enumerate(row):
+                    ev[i][j][0].record(stream)
+                    g.replay()
+                    ev[i][j][1].record(stream)
+            e1.record(stream)
+        barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    images_per_step = BATCH * len(stds)
+    value = world * args.steps * images_per_step / (elapsed_ms * 1e-3)
+    launches = args.steps * len(stds) * 2
+
+    per_std = []
+    total_pair_ms = 0.0
+    for j, s in enumerate(stds):
+        ms = statistics.mean(ev[i][j][0].elapsed_time(ev[i][j][1]) for i in range(args.steps))
+        total_pair_ms += ms
+        gbs = 2 * 2 * plane_bytes / (ms * 1e-3) / 1e9
+        taps = 2 * plans[j][1] + 1
+        per_std.append({"std": s, "taps": taps, "ms_fwd_bwd": round(ms, 4), "images_per_s": round(BATCH / (ms * 1e-3), 1),
+                        "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / hbm_peak, 4)})
+    mean_launch_s = (total_pair_ms * 1e-3) / (2 * len(stds))
+    achieved = 2 * plane_bytes / mean_launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "blur_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+                "traffic": traffic, "kernel": "blur_tile_kernel<1> (fused row+column pass, TMA staged)",
+                "algorithmic_bytes_per_launch": 2 * plane_bytes, "peak_source": peak_src,
+                "note": "mean over the 9-std sweep; above ~25 taps the kernel is FP32-FMA bound, see per_std"}
+
+    # ---- e2e through the public module with host buffers ----------------------------------------------
+    e2e = None
+    if True:
+        xh = torch.empty(BATCH, CH, H, W).uniform_(-1, 1).pin_memory()
+        gh = torch.empty(BATCH, CH, H, W).uniform_(-1, 1).pin_memory()
+        yh = torch.empty(BATCH, CH, H, W).pin_memory()
+        gxh = torch.empty(BATCH, CH, H, W).pin_memory()
+        mod = GaussianBlur(stds[0]).to(dev)
+
+        def e2e_step():
+            for s in stds:
+                mod.set_std(s)
+                x = xh.to(dev, non_blocking=True).requires_grad_(True)
+                y = mod(x)
+                yh.copy_(y.detach(), non_blocking=True)
+                gy = gh.to(dev, non_blocking=True)
+                y.backward(gy)
+                gxh.copy_(x.grad, non_blocking=True)
+
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * e2e_steps * images_per_step / dt, "unit": "images/s",
+               "h2d_bytes_per_step": 2 * plane_bytes * len(stds), "d2h_bytes_per_step": 2 * plane_bytes * len(stds),
+               "steps": e2e_steps, "api": "GaussianBlur(std)(x); y.backward(g) with pinned host x, g -> host y, grad_x"}
+        launches += 0  # e2e launches are outside the timed `value` region
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "stds": stds, "images_per_step": images_per_step, "launches_per_step": 2 * len(stds),
+                   "l2": "5 rotating buffer sets (1.0 GB per GPU) > 126 MB L2; CUDA-graph replay",
+                   "parallelism": "batch sharded, %d x 256 images, no collective" % world},
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "per_std": per_std,
+    }
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(stds)
+    if rank == 0 and not args.no_swd and world == 1:
+        try:
+            line["swd"] = swd_timing(args.swd_images, dev)
+        except Exception as exc:  # secondary measurement: never lose the headline line
+            line["swd"] = {"error": repr(exc)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def swd_timing(n_images, dev):
+    """Secondary: sliced_wasserstein.API on n_images reals + n_images fakes of 3x128x128 (inputs resident in HBM)."""
+    import torch
+
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    mb = 64
+    torch.manual_seed(5)
+    reals = torch.rand(n_images, 3, 128, 128, device=dev) * 2 - 1
+    fakes = (torch.rand(n_images, 3, 128, 128, device=dev) * 2 - 1) * 0.9
+    out = {}
+
+    def run():
+        np.random.seed(0)
+        api = sw.API((3, 128, 128))
+        t = {}
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        api.begin("reals")
+        for i in range(0, n_images, mb):
+            api.feed("reals", reals[i : i + mb])
+        api.end("reals")
+        api.begin("fakes")
+        for i in range(0, n_images, mb):
+            api.feed("fakes", fakes[i : i + mb])
+        torch.cuda.synchronize(dev)
+        t["feed_s"] = time.perf_counter() - t0
+        res = api.end("fakes")
+        torch.cuda.synchronize(dev)
+        t["total_s"] = time.perf_counter() - t0
+        return res, t
+
+    run()  # warm-up
+    res, t = run()
+    rows = n_images * 128
+    out.update({"images_per_set": n_images, "eval_s": round(t["total_s"], 4), "feed_s": round(t["feed_s"], 4),
+                "end_s": round(t["total_s"] - t["feed_s"], 4), "sort_keys": 2 * 4 * 4 * 128 * rows,
+                "sort_gkeys_per_s_incl_project": round(2 * 4 * 4 * 128 * rows / max(t["total_s"] - t["feed_s"], 1e-9) / 1e9, 3),
+                "result_x1e3": [float(v) for v in res], "note": "host RNG draws (reference order) are inside eval_s"})
+    return out
+
+
+def main():
+    args = parse_args()
+    stds = [float(s) for s in args.stds.split(",")] if args.stds else STD_SWEEP
+    if args.impl == "reference":
+        run_reference_arm(args, stds)
+    else:
+        run_native(args, stds)
+
+
+if __name__ == "__main__":
+    main()

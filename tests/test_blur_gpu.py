@@ -1,0 +1,239 @@
+"""GPU parity tests of the blur: CUDA path (through the public modules -> custom op -> C ABI) against
+the CPU oracle and the golden vectors of the unmodified reference.
+
+Tolerance (BASELINE.json north_star): <= 1e-5 relative on blurred pixels and gradients, measured as
+max|got - want| / max|want| (the blurred field of a zero-mean input has values arbitrarily close to 0,
+so a per-element relative error is not meaningful), plus an element-wise allclose(rtol=1e-5, atol=2e-6*scale).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import uniform_pm1
+from oracle import blur_oracle as bo
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def assert_close(got, want, what=""):
+    got = got.detach().cpu().numpy() if torch.is_tensor(got) else got
+    scale = max(float(np.abs(want).max()), 1e-6)
+    err = float(np.abs(got - want).max()) / scale
+    assert err <= RTOL, "%s: relative error %.3g > %g" % (what, err, RTOL)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=2e-6 * scale, err_msg=what)
+
+
+from test_oracle_blur import FLAT  # noqa: E402  (same cases as the golden file)
+
+
+@pytest.mark.parametrize("name,shape,std", FLAT)
+def test_torch_module_matches_reference_golden(golden_blur, name, shape, std):
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = _dev(uniform_pm1(1234, shape)).requires_grad_(True)
+    g = _dev(uniform_pm1(4321, shape))
+    mod = GaussianBlur(std).cuda()
+    y = mod(x)
+    y.backward(g)
+    key = "%s_std%g" % (name, std)
+    assert_close(y, golden_blur[key + "_y"], key + " forward")
+    assert_close(x.grad, golden_blur[key + "_gx"], key + " input gradient")
+    assert mod.kernel_size == len(golden_blur[key + "_taps"])
+
+
+def test_device_taps_match_reference(golden_taps):
+    from blurred_gan_b200 import ops
+
+    for std, h, w, k in golden_taps["rows"]:
+        ref = golden_taps["taps_%g_%d_%d" % (std, h, w)]
+        got = ops.device_taps(ops.RULE_TORCH, float(std), int(k) // 2, "cuda").cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-9, err_msg="std=%g k=%d" % (std, k))
+    for std, size in [(0.01, 128), (0.5, 128), (5, 128), (23, 128), (64, 1024)]:
+        k, r, s = bo.tf_rule_plan(std, size, size)
+        got = ops.device_taps(ops.RULE_TF, s, r, "cuda").cpu().numpy()
+        np.testing.assert_allclose(got, bo.tf_rule_taps(s, 2 * r + 1), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("std", [0.01, 0.5, 1.0, 2.0, 3.0, 5.0, 8.0, 12.0, 16.0, 23.0])
+def test_celeba_shape_nchw_torch_rule(std):
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(0, (4, 3, 128, 128))
+    want = bo.gaussian_blur_torch_ref(x, std)
+    assert_close(GaussianBlur(std).cuda()(_dev(x)), want, "std=%g" % std)
+
+
+@pytest.mark.parametrize("std", [0.01, 0.5, 1.0, 2.0, 5.0, 8.0, 16.0, 23.0])
+@pytest.mark.parametrize("layout", ["NHWC", "NCHW"])
+def test_celeba_shape_tf_rule(std, layout):
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D, blur_images
+
+    shape = (3, 128, 128, 3) if layout == "NHWC" else (3, 3, 128, 128)
+    x = uniform_pm1(1, shape)
+    want = bo.blur_images_tf_ref(x, std)
+    assert_close(blur_images(_dev(x), std), want, "%s std=%g" % (layout, std))
+    layer = GaussianBlur2D(std).cuda()
+    assert_close(layer(_dev(x)), want, "layer %s std=%g" % (layout, std))
+
+
+def test_mnist_shape_annealed_std():
+    """BASELINE configs[0]: 64 x 28 x 28 x 1 with std annealed 23 -> 0, both APIs."""
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(2, (64, 1, 28, 28))
+    xd = _dev(x)
+    mod = GaussianBlur(23.0).cuda()
+    layer = GaussianBlur2D(23.0).cuda()
+    x_nhwc = np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+    for std in np.linspace(23.0, 0.02, 12):
+        std = float(std)
+        mod.set_std(std)
+        assert_close(mod(xd), bo.gaussian_blur_torch_ref(x, std), "torch std=%g" % std)
+        layer.assign(std)
+        assert_close(layer(_dev(x_nhwc)), bo.blur_images_tf_ref(x_nhwc, std), "tf std=%g" % std)
+
+
+@pytest.mark.parametrize("shape,layout", [((2, 3, 37, 50), "NCHW"), ((2, 31, 45, 3), "NHWC"), ((3, 2, 5, 9), "NCHW"),
+                                          ((1, 1, 16, 300), "NCHW"), ((2, 130, 66, 1), "NHWC"), ((1, 5, 200, 36), "NCHW"),
+                                          ((1, 3, 129, 131), "NCHW"), ((1, 40, 260, 3), "NHWC")])
+def test_ragged_shapes_both_rules(shape, layout):
+    from blurred_gan_b200.gaussian_blur import blur_images
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(5, shape)
+    for std in (0.4, 1.7, 4.0, 9.0, 30.0):
+        if bo.get_data_format(shape) == layout:
+            assert_close(blur_images(_dev(x), std), bo.blur_images_tf_ref(x, std), "tf %s std=%g" % (shape, std))
+        if layout == "NCHW":
+            assert_close(GaussianBlur(std).cuda()(_dev(x)), bo.gaussian_blur_torch_ref(x, std), "torch %s std=%g" % (shape, std))
+
+
+@pytest.mark.parametrize("std", [8.0, 32.0, 64.0])
+def test_large_image_wide_halo(std):
+    """BASELINE configs[3] shape (1024 x 1024, std up to 64), reduced batch for the CPU oracle."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import blur_images
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(6, (1, 2, 1024, 1024))
+    assert_close(GaussianBlur(std).cuda()(_dev(x)), bo.gaussian_blur_torch_ref(x, std), "torch 1024 std=%g" % std)
+    if std >= 32.0:
+        assert ops.last_blur_path() == 3  # row pass + column pass through scratch
+    xh = uniform_pm1(7, (1, 1024, 1024, 3))
+    assert_close(blur_images(_dev(xh), std), bo.blur_images_tf_ref(xh, std), "tf NHWC 1024 std=%g" % std)
+
+
+def test_tma_and_plain_staging_agree_bitwise():
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = _dev(uniform_pm1(8, (5, 3, 128, 128)))
+    for std in (0.5, 2.0, 5.0, 23.0):
+        mod = GaussianBlur(std).cuda()
+        os.environ.pop("BGAN_BLUR_NO_TMA", None)
+        y_tma = mod(x)
+        path_tma = ops.last_blur_path()
+        os.environ["BGAN_BLUR_NO_TMA"] = "1"
+        try:
+            y_plain = mod(x)
+            path_plain = ops.last_blur_path()
+        finally:
+            os.environ.pop("BGAN_BLUR_NO_TMA", None)
+        assert path_tma == 1 and path_plain == 2
+        assert torch.equal(y_tma, y_plain)
+
+
+@pytest.mark.parametrize("th,tw", [(32, 64), (64, 128), (16, 32), (128, 64)])
+def test_tilings_agree(th, tw):
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = _dev(uniform_pm1(9, (3, 2, 128, 128)))
+    for std in (1.0, 5.0):
+        mod = GaussianBlur(std).cuda()
+        want = mod(x)
+        os.environ["BGAN_BLUR_TH"], os.environ["BGAN_BLUR_TW"] = str(th), str(tw)
+        try:
+            got = mod(x)
+        finally:
+            os.environ.pop("BGAN_BLUR_TH"), os.environ.pop("BGAN_BLUR_TW")
+        assert_close(got, want.cpu().numpy(), "tile %dx%d std=%g" % (th, tw, std))
+
+
+def test_double_backward_gradient_penalty_pattern():
+    """The WGAN-GP critic step differentiates through the input-gradient (reference wgan.py:234-246, :140)."""
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    std = 2.0
+    x_np, w_np, z_np = uniform_pm1(10, (2, 3, 32, 40)), uniform_pm1(11, (2, 3, 32, 40)), uniform_pm1(12, (2, 3, 32, 40))
+    x = _dev(x_np).requires_grad_(True)
+    w = _dev(w_np).requires_grad_(True)
+    mod = GaussianBlur(std).cuda()
+    y = mod(x)
+    (gx,) = torch.autograd.grad((y * w).sum(), x, create_graph=True)  # gx = B w
+    assert_close(gx, bo.gaussian_blur_torch_ref(w_np, std), "first-order")
+    (gw,) = torch.autograd.grad((gx * _dev(z_np)).sum(), w)  # d/dw <B w, z> = B z
+    assert_close(gw, bo.gaussian_blur_torch_ref(z_np, std), "double backward")
+
+
+def test_explicit_taps_op_and_asymmetric_adjoint():
+    from blurred_gan_b200 import ops
+
+    x_np = uniform_pm1(13, (2, 2, 24, 28))
+    taps = bo.taps_for(bo.RULE_TORCH, 2.0, 24, 28)
+    got = ops.blur2d_taps(_dev(x_np), _dev(taps), ops.LAYOUT_NCHW)
+    assert_close(got, bo.blur_nchw(x_np, taps), "explicit symmetric taps")
+    asym = np.float32([0.1, 0.2, 0.4, 0.25, 0.05])
+    x = _dev(x_np).requires_grad_(True)
+    y = ops.blur2d_taps(x, _dev(asym), ops.LAYOUT_NCHW)
+    assert_close(y, bo.blur_nchw(x_np, asym), "explicit asymmetric taps")
+    g_np = uniform_pm1(14, x_np.shape)
+    y.backward(_dev(g_np))
+    assert_close(x.grad, bo.blur_nchw(g_np, asym[::-1].copy()), "adjoint of asymmetric taps")
+
+
+@pytest.mark.parametrize("std", [0.5, 5.0, 23.0])
+def test_full_size_properties(std):
+    """BASELINE configs[1] at full size (256 x 3 x 128 x 128): size-independent properties."""
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    torch.manual_seed(0)
+    x = torch.rand(256, 3, 128, 128, device="cuda") * 2 - 1
+    y = torch.rand(256, 3, 128, 128, device="cuda") * 2 - 1
+    mod = GaussianBlur(std).cuda()
+    bx, by = mod(x), mod(y)
+    # self-adjoint: <Bx, y> == <x, By>
+    lhs, rhs = (bx.double() * y.double()).sum().item(), (x.double() * by.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+    # linear
+    z = mod(2.0 * x - 0.5 * y)
+    assert (z - (2.0 * bx - 0.5 * by)).abs().max().item() <= 1e-5 * max(bx.abs().max().item(), 1e-3) * 3
+    # every plane is treated alike: plane 700 alone == plane 700 of the batch
+    single = mod(x.view(768, 1, 128, 128)[700:701])
+    assert torch.equal(single[0, 0], bx.view(768, 128, 128)[700])
+    # a few planes against the oracle
+    idx = [0, 383, 767]
+    want = bo.gaussian_blur_torch_ref(x.view(768, 1, 128, 128)[idx].cpu().numpy(), std)
+    assert_close(bx.view(768, 1, 128, 128)[idx], want, "full-size spot check")
+
+
+def test_ones_image_border_profile_and_errors():
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    y = GaussianBlur(2.0).cuda()(torch.ones(1, 1, 64, 64, device="cuda"))
+    assert y[0, 0, 0, 0].item() == pytest.approx(0.310, abs=2e-3) and y[0, 0, 32, 32].item() == pytest.approx(1.0, abs=1e-6)
+    with pytest.raises(RuntimeError):
+        ops.blur2d(torch.zeros(2, 8, 8, 2, device="cuda"), ops.LAYOUT_NHWC, ops.RULE_TF, 1.0, 1)  # NHWC needs C in {1,3}
+    assert GaussianBlur(1.0).cuda()(torch.zeros(0, 3, 8, 8, device="cuda")).shape == (0, 3, 8, 8)
+    # non-contiguous input is accepted
+    xt = torch.rand(2, 16, 20, 3, device="cuda").permute(0, 3, 1, 2)
+    assert_close(GaussianBlur(1.0).cuda()(xt), bo.gaussian_blur_torch_ref(xt.cpu().numpy(), 1.0), "permuted view")

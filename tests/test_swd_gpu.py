@@ -1,0 +1,171 @@
+"""GPU parity tests of the SWD kernels against the CPU oracle and the reference's golden vectors.
+Integer / gather / sort work is bit-exact; the pyramid is bit-exact (fp64 accumulate, one rounding);
+floating-point reductions are within 1e-6; the SWD distances within north_star's 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import uniform_pm1
+from oracle import swd_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("shape", [(5, 3, 64, 64), (2, 3, 128, 128), (1, 3, 16, 16), (2, 3, 32, 48)])
+def test_pyramid_bit_exact(shape):
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    x = uniform_pm1(3, shape)
+    levels = 1
+    while min(shape[2], shape[3]) // (2 ** levels) >= 8 and levels < 4:
+        levels += 1
+    xd = _dev(x)
+    keep = xd.clone()
+    got = sw.generate_laplacian_pyramid(xd, levels)
+    assert torch.equal(xd, keep)  # inputs are not mutated
+    want = so.generate_laplacian_pyramid(x, levels)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+    np.testing.assert_array_equal(sw.reconstruct_laplacian_pyramid(got).cpu().numpy(), so.reconstruct_laplacian_pyramid(want))
+
+
+def test_pyr_down_up_odd_sizes_and_golden(golden_swd):
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    for shape in [(1, 3, 17, 31), (2, 1, 5, 6), (1, 2, 1, 9), (1, 1, 2, 2)]:
+        x = uniform_pm1(4, shape)
+        np.testing.assert_array_equal(sw.pyr_down(x).cpu().numpy(), so.pyr_down(x))
+        np.testing.assert_array_equal(sw.pyr_up(x).cpu().numpy(), so.pyr_up(x))
+    reals = uniform_pm1(11, (6, 3, 64, 64))
+    np.testing.assert_array_equal(sw.pyr_down(reals).cpu().numpy(), golden_swd["s64_down"])
+    np.testing.assert_array_equal(sw.pyr_up(golden_swd["s64_down"]).cpu().numpy(), golden_swd["s64_up"])
+    for i, lvl in enumerate(sw.generate_laplacian_pyramid(reals, 3)):
+        np.testing.assert_array_equal(lvl.cpu().numpy(), golden_swd["s64_pyr%d" % i])
+
+
+def test_descriptor_gather_exact_and_statistics(golden_swd):
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    level0 = golden_swd["s64_pyr0"]
+    np.random.seed(7)
+    desc = sw.get_descriptors_for_minibatch(level0, 7, 128)
+    assert tuple(desc.shape) == (6 * 128, 3, 7, 7)
+    np.testing.assert_array_equal(desc[:256].cpu().numpy(), golden_swd["s64_desc0"])
+    want = so.gather_descriptors(level0, golden_swd["s64_px"], golden_swd["s64_py"], 7, 128)
+    np.testing.assert_array_equal(desc.cpu().numpy(), want)
+    sums = torch.zeros(6, dtype=torch.float64, device="cuda")
+    ops.swd_extract(_dev(level0), golden_swd["s64_px"], golden_swd["s64_py"], 128, 7, sums)
+    w64 = want.astype(np.float64)
+    np.testing.assert_allclose(sums.cpu().numpy(), np.concatenate([w64.sum((0, 2, 3)), (w64 ** 2).sum((0, 2, 3))]), rtol=1e-12)
+    fin = sw.finalize_descriptors(desc)
+    assert tuple(fin.shape) == (768, 147)
+    np.testing.assert_allclose(fin[:256].cpu().numpy(), golden_swd["s64_final0"], rtol=2e-6, atol=2e-6)
+    fin2 = sw.finalize_descriptors([desc[:300], desc[300:]])
+    assert torch.equal(fin, fin2)
+
+
+@pytest.mark.parametrize("rows,k,d", [(1000, 147, 128), (129, 147, 512), (5, 7, 3), (4096, 147, 64), (300, 49, 130)])
+def test_projection(rows, k, d):
+    from blurred_gan_b200 import ops
+
+    rs = np.random.RandomState(rows)
+    A = rs.randn(rows, k).astype(np.float32)
+    dirs = rs.randn(k, d).astype(np.float32)
+    got = ops.swd_project(_dev(A), _dev(dirs)).cpu().numpy()
+    want = (A.astype(np.float64) @ dirs.astype(np.float64)).T
+    assert got.shape == (d, rows)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("segments,rows", [(1, 1), (3, 5), (2, 4096), (5, 4097), (130, 1000), (4, 100000), (1, 1 << 20)])
+def test_segmented_sort_is_exact(segments, rows):
+    from blurred_gan_b200 import ops
+
+    rs = np.random.RandomState(segments * 7919 + rows)
+    keys = (rs.randn(segments, rows) * 10.0 ** rs.randint(-3, 4, size=(segments, 1))).astype(np.float32)
+    if rows >= 5:
+        keys[:, 0] = 0.0
+        keys[:, 1] = -0.0
+        keys[:, 2] = keys[:, 3]
+        keys[0, 4] = np.inf
+        keys[-1, 4] = -np.inf
+    got = ops.swd_sort_(_dev(keys)).cpu().numpy()
+    want = np.sort(keys, axis=1)
+    np.testing.assert_array_equal(got, want)  # (-0.0 == 0.0 compares equal; order among them is irrelevant)
+
+
+def test_absdiff_sum():
+    from blurred_gan_b200 import ops
+
+    a, b = uniform_pm1(1, (128, 3001)), uniform_pm1(2, (128, 3001))
+    got = ops.swd_absdiff_sum(_dev(a), _dev(b)).item()
+    want = np.abs(a.astype(np.float64) - b.astype(np.float64)).sum()
+    # |a-b| is formed in fp32 like the reference's np.abs(projA - projB), then summed in fp64
+    assert got == pytest.approx(np.abs(a - b).astype(np.float64).sum(), rel=1e-12)
+    assert got == pytest.approx(want, rel=1e-6)
+
+
+def test_sliced_wasserstein_known_answer(golden_swd):
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    rs = np.random.RandomState(5)
+    A = rs.randn(1000, 147).astype(np.float32)
+    B = (rs.randn(1000, 147) * 1.2 + 0.1).astype(np.float32)
+    np.random.seed(9)
+    got = sw.sliced_wasserstein(A, B, 4, 128)
+    assert got == pytest.approx(golden_swd["sw_AB"][0], rel=1e-4)
+    np.random.seed(1)
+    assert sw.sliced_wasserstein(A, A, 2, 16) == 0.0
+
+
+def _run_api(api, reals, fakes, mb, as_tensor=False):
+    conv = (lambda a: torch.from_numpy(a).cuda()) if as_tensor else (lambda a: a.copy())
+    api.begin("reals")
+    for i in range(0, len(reals), mb):
+        api.feed("reals", conv(reals[i : i + mb]))
+    r0 = api.end("reals")
+    api.begin("fakes")
+    for i in range(0, len(fakes), mb):
+        api.feed("fakes", conv(fakes[i : i + mb]))
+    return np.array(r0, np.float64), np.array(api.end("fakes"), np.float64)
+
+
+@pytest.mark.parametrize("as_tensor", [False, True])
+def test_api_matches_reference_golden(golden_swd, as_tensor):
+    """Identical seeds -> identical patches and projections; distances within 1e-4 (north_star)."""
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    reals = uniform_pm1(11, (6, 3, 64, 64))
+    fakes = (0.8 * uniform_pm1(12, (6, 3, 64, 64)) + 0.1).astype(np.float32)
+    np.random.seed(0)
+    r0, r1 = _run_api(sw.API((3, 64, 64)), reals, fakes, 3, as_tensor)
+    np.testing.assert_array_equal(r0, golden_swd["s64_api_reals"])
+    np.testing.assert_allclose(r1, golden_swd["s64_api_fakes"], rtol=1e-4)
+
+    reals = uniform_pm1(21, (16, 3, 128, 128))
+    fakes = np.clip(uniform_pm1(22, (16, 3, 128, 128)) * 1.1 - 0.05, -1, 1).astype(np.float32)
+    np.random.seed(0)
+    r0, r1 = _run_api(sw.API((3, 128, 128)), reals, fakes, 8, as_tensor)
+    np.testing.assert_array_equal(r0, golden_swd["s128_api_reals"])
+    np.testing.assert_allclose(r1, golden_swd["s128_api_fakes"], rtol=1e-4)
+    assert len(r1) == 5 and r1[4] == pytest.approx(np.mean(r1[:4]), rel=1e-6)
+
+
+def test_api_matches_oracle_larger():
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    reals = uniform_pm1(31, (96, 3, 128, 128))
+    fakes = (0.9 * uniform_pm1(32, (96, 3, 128, 128))).astype(np.float32)
+    fakes[:, :, ::2] *= 0.8
+    np.random.seed(3)
+    want = _run_api(so.API((3, 128, 128)), reals, fakes, 32)
+    np.random.seed(3)
+    got = _run_api(sw.API((3, 128, 128)), reals, fakes, 32)
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-4)
