@@ -126,7 +126,7 @@ def test_large_image_wide_halo(std):
 
     x = uniform_pm1(6, (1, 2, 1024, 1024))
     assert_close(GaussianBlur(std).cuda()(_dev(x)), bo.gaussian_blur_torch_ref(x, std), "torch 1024 std=%g" % std)
-    if std >= 32.0:
+    if std >= 64.0:
         assert ops.last_blur_path() == 3  # row pass + column pass through scratch
     xh = uniform_pm1(7, (1, 1024, 1024, 3))
     assert_close(blur_images(_dev(xh), std), bo.blur_images_tf_ref(xh, std), "tf NHWC 1024 std=%g" % std)
