@@ -25,15 +25,20 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "taps.cuh"
 
 namespace bgan {
+
+// blur_tc.cu: tcgen05 path for 128 x 128 planes
+bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, const float* x, const float* y);
+int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff, int radius, cudaStream_t stream);
+
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTO = 16;  // outputs per thread along the filtered axis (both passes)
 constexpr int kK = 8;    // taps per register chunk
-constexpr float kSqrt2Pi = 2.5066282746310002f;
 
 struct BlurArgs {
     const float* x;
@@ -54,41 +59,6 @@ struct BlurArgs {
     int box_rows, nbox;  // TMA: in_rows = box_rows * nbox
     int64_t units;
 };
-
-// ---------------------------------------------------------------------------------------------
-// taps (reference pytorch/gaussianblur.py:9-14 and gaussian_blur.py:83-88), normalised to sum 1
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float raw_tap(int rule, float s, int i) {
-    const float x = static_cast<float>(i);
-    if (rule == BGAN_RULE_TORCH) {
-        // g = exp(-(x^2 / (2 s^2)) / (sqrt(2 pi) s)) -- the normaliser sits inside the exp
-        const float num = (x * x) / (2.0f * (s * s));
-        const float den = kSqrt2Pi * s;
-        return expf(-(num / den));
-    }
-    // g = exp(-(x^2 / (2 s^2))) / (sqrt(2 pi) s)
-    return expf(-((x * x) / (2.0f * (s * s)))) / (kSqrt2Pi * s);
-}
-
-// Fills s_g[0 .. 2r] with normalised taps; s_red is one double of scratch.  All threads call it.
-__device__ void normalised_taps(int rule, float s, int r, const float* __restrict__ taps_dev, float* s_g, double* s_red) {
-    const int n = 2 * r + 1;
-    for (int t = threadIdx.x; t < n; t += blockDim.x)
-        s_g[t] = (rule == BGAN_RULE_EXPLICIT) ? taps_dev[t] : raw_tap(rule, s, t - r);
-    __syncthreads();
-    if (rule != BGAN_RULE_EXPLICIT) {
-        if (threadIdx.x < 32) {
-            double acc = 0.0;
-            for (int t = threadIdx.x; t < n; t += 32) acc += static_cast<double>(s_g[t]);
-            acc = warp_sum(acc);
-            if (threadIdx.x == 0) *s_red = acc;
-        }
-        __syncthreads();
-        const float total = static_cast<float>(*s_red);
-        for (int t = threadIdx.x; t < n; t += blockDim.x) s_g[t] = s_g[t] / total;
-        __syncthreads();
-    }
-}
 
 __global__ void taps_kernel(int rule, float s, int r, float* __restrict__ out) {
     extern __shared__ float s_dyn[];
@@ -582,6 +552,10 @@ extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int heigh
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     bool tma = false;
 
+    if (blur_tc_eligible(g.planes, g.H, g.Wc, g.ES, radius, rule, x, y)) {
+        g_last_path = 4;
+        return blur_tc_launch(x, y, g.planes, rule, std_eff, radius, stream);
+    }
     Plan fused = choose_plan(g.H, g.Wc, g.ES, radius, radius);
     if (fused.ok) {
         int rc = launch_any(fused, g.ES, x, y, g.planes, rule, std_eff, taps_device, stream, &tma);

@@ -1,0 +1,343 @@
+// Tensor-core Gaussian blur for 128 x 128 planes (sm_100a: tcgen05.mma + TMEM + TMA).
+//
+// For one plane X [h][w] the separable zero-padded blur is  Y = T X T  with T the symmetric banded
+// Toeplitz matrix of the taps (T[i][j] = tap[j - i + r] for |i - j| <= r).  Written as two
+// 128 x 128 x 128 GEMMs the cost no longer depends on the tap count, which turns the FP32-FMA-bound
+// wide blurs (sigma >= 3: 30 .. 258 FMAs per pixel on CUDA cores) into HBM-bound work.
+//
+// fp32 parity (<= 1e-5) on fp16 tensor cores: error-compensated split.  Every operand is written as
+// a = a1 + 2^-11 a2 with a1 = fp16(a), a2 = fp16((a - a1) 2^11), and
+//     A B ~= A1 B1 + 2^-11 (A1 B2 + A2 B1)                         (the dropped term is 2^-22 A2 B2)
+// accumulated in fp32 in TMEM: the cross terms first, then A1 B1 with the accumulator pre-scaled by
+// 2^-11 through tcgen05.mma's scale-input-d operand.  Planes are rescaled by a power of two so that
+// max|x| lands in [2^12, 2^13) -- exact in fp32, keeps every piece inside fp16's normal range for any
+// input magnitude -- and the inverse is applied to the output.  Measured error vs fp64: ~3e-7, the
+// same as the fp32 FMA path (tests/test_blur_gpu.py).
+//
+// Orientation.  Both GEMMs produce transposed results so that no explicit transpose is needed and
+// the final store is coalesced:
+//   GEMM1  D1[w'][h]  = sum_w T[w'][w] X[h][w]      A = T (K-major)    B = X (K-major: row h, K = w)
+//   GEMM2  D2[w'][h'] = sum_h D1[w'][h] T[h][h']    A = D1 split to fp16 (row w', K = h)   B = T
+// D2 = Y^T sits in TMEM with lane = w': for a fixed register (h') the 32 lanes of a warp hold 32
+// consecutive w' -> one coalesced 128-byte store per instruction.
+//
+// Per CTA (persistent, one per SM): TMA box load of the next fp32 plane into a staging buffer overlaps
+// everything after the conversion of the current one.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "taps.cuh"
+
+namespace bgan {
+namespace {
+
+constexpr int kP = 128;  // plane edge
+constexpr int kTcThreads = 256;
+// operand tile: K-major, no swizzle, core matrix = 8 rows x 16 bytes.  Core matrices adjacent in K are
+// 144 bytes apart (16 bytes of padding) so that a warp writing consecutive K-chunks of one row, or
+// consecutive rows of one chunk, never hits a bank twice.
+constexpr uint32_t kLBO = 144;              // K-adjacent core matrices
+constexpr uint32_t kSBO = 16 * kLBO;        // row-group (8 rows) stride = 2304
+constexpr uint32_t kTileBytes = 16 * kSBO;  // 36864
+constexpr uint32_t kOffStage = 0;           // fp32 plane, TMA destination (64 KB)
+constexpr uint32_t kOffT1 = 65536;
+constexpr uint32_t kOffT2 = kOffT1 + kTileBytes;
+constexpr uint32_t kOffO1 = kOffT2 + kTileBytes;  // X1, later Z1
+constexpr uint32_t kOffO2 = kOffO1 + kTileBytes;  // X2, later Z2
+constexpr uint32_t kOffMisc = kOffO2 + kTileBytes;
+constexpr uint32_t kSmemTc = kOffMisc + 1024 /* taps */ + 128;
+constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
+// instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, N = 128, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct TcArgs {
+    float* y;
+    int planes;
+    int rule;
+    float std_eff;
+    int radius;
+};
+
+__device__ __forceinline__ uint32_t tile_off(int row, int k) {
+    return (row >> 3) * kSBO + (k >> 3) * kLBO + (row & 7) * 16 + (k & 7) * 2;
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(kLBO >> 4) << 16) |
+           (static_cast<uint64_t>(kSBO >> 4) << 32) | (1ull << 46);  // version 1, SWIZZLE_NONE, base offset 0
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+// D = A B + D * 2^-11
+__device__ __forceinline__ void umma_f16_scale_d11(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p, 11;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// a -> (fp16(a), fp16((a - fp16(a)) * 2^11)) for two values at a time
+__device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hi);
+    lo = __floats2half2_rn((a - back.x) * kLoScale, (b - back.y) * kLoScale);
+}
+
+// the three products of one GEMM into one accumulator: cross terms, then the main term on the
+// accumulator pre-scaled by 2^-11.  Each product is 8 instructions of K = 16.
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a1, uint32_t a2, uint32_t b1, uint32_t b2) {
+    const uint64_t da1 = smem_desc(a1), da2 = smem_desc(a2), db1 = smem_desc(b1), db2 = smem_desc(b2);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;  // 16 K-elements = 2 core matrices, in 16-byte units
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_f16(d_tmem, da1 + k * kStep, db2 + k * kStep, k > 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_f16(d_tmem, da2 + k * kStep, db1 + k * kStep, 1);
+    umma_f16_scale_d11(d_tmem, da1, db1);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) umma_f16(d_tmem, da1 + k * kStep, db1 + k * kStep, 1);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* stage = reinterpret_cast<float*>(smem + kOffStage);
+    float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
+    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kOffMisc + 1024);
+    uint64_t* mbar_mma = mbar_tma + 1;
+    double* s_red = reinterpret_cast<double*>(mbar_tma + 2);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 3);
+    float* s_max = reinterpret_cast<float*>(mbar_tma + 4);  // 8 floats
+    const uint32_t sbase = smem_u32(smem);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(mbar_tma, 1);
+        mbar_init(mbar_mma, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) {  // 256 TMEM columns: D1 = [0, 128), D2 = [128, 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- T1, T2: banded Toeplitz operand tiles, built once per CTA -------------------------------------
+    normalised_taps(a.rule, a.std_eff, a.radius, nullptr, s_g, s_red);  // syncs inside
+    for (int idx = tid; idx < kP * 16; idx += kTcThreads) {
+        const int row = idx & 127, chunk = idx >> 7;  // lanes <-> consecutive rows: conflict-free 16-byte stores
+        __half2 hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k0 = chunk * 8 + 2 * e;
+            const int d0 = k0 - row + a.radius, d1 = d0 + 1;
+            const float t0 = (d0 >= 0 && d0 <= 2 * a.radius) ? s_g[d0] : 0.0f;
+            const float t1 = (d1 >= 0 && d1 <= 2 * a.radius) ? s_g[d1] : 0.0f;
+            split2(t0, t1, hi[e], lo[e]);
+        }
+        const uint32_t off = tile_off(row, chunk * 8);
+        *reinterpret_cast<uint4*>(smem + kOffT1 + off) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(smem + kOffT2 + off) = *reinterpret_cast<uint4*>(lo);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t d1 = tmem, d2 = tmem + 128;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+    const int col_half = (warp >> 2) * 64;
+
+    uint32_t par_tma = 0, par_mma = 0;
+    if (tid == 0 && blockIdx.x < a.planes) {
+        mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+        tma_load_3d(stage, &tmap, mbar_tma, 0, 0, blockIdx.x);
+    }
+
+    for (int p = blockIdx.x; p < a.planes; p += gridDim.x) {
+        // ---- fp32 plane -> registers, plane max ---------------------------------------------------------
+        mbar_wait(mbar_tma, par_tma);
+        par_tma ^= 1;
+        float4 v[16];
+        float m = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            v[j] = *reinterpret_cast<const float4*>(stage + (j * kTcThreads + tid) * 4);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_max[warp] = m;
+        __syncthreads();  // staging drained, s_max visible; the previous plane's GEMM2 has completed (waited in its epilogue)
+        if (tid == 0 && p + gridDim.x < a.planes) {
+            mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+            tma_load_3d(stage, &tmap, mbar_tma, 0, 0, p + gridDim.x);
+        }
+        m = s_max[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w]);
+        // power-of-two scale putting max|x| in [2^12, 2^13)
+        int eb = (__float_as_int(m) >> 23) & 0xff;
+        eb = min(max(eb, 13), 254);
+        const float scale = __int_as_float((266 - eb) << 23);
+        const float inv_scale = __int_as_float((eb - 12) << 23);
+
+        // ---- X1, X2 (B operand of GEMM1: row = h, K = w) ---------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int f = j * kTcThreads + tid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
+            const int h = f >> 5, w = (f & 31) << 2;
+            __half2 hi[2], lo[2];
+            split2(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
+            split2(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
+            const uint32_t off = tile_off(h, w);
+            *reinterpret_cast<uint2*>(smem + kOffO1 + off) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(smem + kOffO2 + off) = *reinterpret_cast<uint2*>(lo);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, sbase + kOffO1, sbase + kOffO2);  // D1 = T X^T
+            umma_commit(mbar_mma);
+        }
+        mbar_wait(mbar_mma, par_mma);
+        par_mma ^= 1;
+        tc_fence_after();
+
+        // ---- D1 -> Z1, Z2 (A operand of GEMM2: row = w', K = h); X tiles are dead once GEMM1 has completed -----
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            float z[32];
+            const int h0 = col_half + cc * 32;
+            tmem_ld32(d1 + lane_base + h0, z);
+            const int row = (warp & 3) * 32 + lane;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                __half2 hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2(z[c8 * 8 + 2 * e], z[c8 * 8 + 2 * e + 1], hi[e], lo[e]);
+                const uint32_t off = tile_off(row, h0 + c8 * 8);
+                *reinterpret_cast<uint4*>(smem + kOffO1 + off) = *reinterpret_cast<uint4*>(hi);
+                *reinterpret_cast<uint4*>(smem + kOffO2 + off) = *reinterpret_cast<uint4*>(lo);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(d2, sbase + kOffO1, sbase + kOffO2, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
+            umma_commit(mbar_mma);
+        }
+        mbar_wait(mbar_mma, par_mma);
+        par_mma ^= 1;
+        tc_fence_after();
+
+        // ---- D2 = Y^T -> global, coalesced along w' ---------------------------------------------------------
+        float* yp = a.y + static_cast<size_t>(p) * kP * kP + (warp & 3) * 32 + lane;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            float o[32];
+            const int h0 = col_half + cc * 32;
+            tmem_ld32(d2 + lane_base + h0, o);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(h0 + j) * kP, o[j] * inv_scale);
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+}  // namespace
+
+bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, const float* x, const float* y) {
+    const char* off = getenv("BGAN_BLUR_NO_TC");
+    if (off && atoi(off)) return false;
+    const char* min_r = getenv("BGAN_BLUR_TC_MIN_R");
+    const int rmin = min_r ? atoi(min_r) : 0;
+    return ES == 1 && H == kP && Wc == kP && planes > 0 && radius >= rmin && radius <= 127 &&
+           (rule == BGAN_RULE_TORCH || rule == BGAN_RULE_TF) && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+           reinterpret_cast<uintptr_t>(y) % 16 == 0 && encode_fn() != nullptr;
+}
+
+int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff, int radius, cudaStream_t stream) {
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const cuuint64_t dims[3] = {kP, kP, static_cast<cuuint64_t>(planes)};
+    const cuuint64_t strides[2] = {kP * 4, kP * kP * 4};
+    const cuuint32_t box[3] = {kP, kP, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult res = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
+    thread_local int attr_dev = -1;
+    int dev = 0;
+    BGAN_CUDA_OK(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        attr_dev = dev;
+    }
+    TcArgs a{y, planes, rule, std_eff, radius};
+    const unsigned grid = static_cast<unsigned>(std::min(planes, device_sm_count()));
+    blur_tc128_kernel<<<grid, kTcThreads, kSmemTc, stream>>>(a, tmap);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace bgan

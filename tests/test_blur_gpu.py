@@ -137,6 +137,7 @@ def test_tma_and_plain_staging_agree_bitwise():
     from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
 
     x = _dev(uniform_pm1(8, (5, 3, 128, 128)))
+    os.environ["BGAN_BLUR_NO_TC"] = "1"  # this test is about the CUDA-core tile kernel
     for std in (0.5, 2.0, 5.0, 23.0):
         mod = GaussianBlur(std).cuda()
         os.environ.pop("BGAN_BLUR_NO_TMA", None)
@@ -148,6 +149,8 @@ def test_tma_and_plain_staging_agree_bitwise():
             path_plain = ops.last_blur_path()
         finally:
             os.environ.pop("BGAN_BLUR_NO_TMA", None)
+            if std == 23.0:
+                os.environ.pop("BGAN_BLUR_NO_TC", None)
         assert path_tma == 1 and path_plain == 2
         assert torch.equal(y_tma, y_plain)
 
@@ -159,12 +162,13 @@ def test_tilings_agree(th, tw):
     x = _dev(uniform_pm1(9, (3, 2, 128, 128)))
     for std in (1.0, 5.0):
         mod = GaussianBlur(std).cuda()
-        want = mod(x)
-        os.environ["BGAN_BLUR_TH"], os.environ["BGAN_BLUR_TW"] = str(th), str(tw)
+        os.environ["BGAN_BLUR_NO_TC"] = "1"
         try:
+            want = mod(x)
+            os.environ["BGAN_BLUR_TH"], os.environ["BGAN_BLUR_TW"] = str(th), str(tw)
             got = mod(x)
         finally:
-            os.environ.pop("BGAN_BLUR_TH"), os.environ.pop("BGAN_BLUR_TW")
+            os.environ.pop("BGAN_BLUR_TH", None), os.environ.pop("BGAN_BLUR_TW", None), os.environ.pop("BGAN_BLUR_NO_TC", None)
         assert_close(got, want.cpu().numpy(), "tile %dx%d std=%g" % (th, tw, std))
 
 
@@ -237,3 +241,35 @@ def test_ones_image_border_profile_and_errors():
     # non-contiguous input is accepted
     xt = torch.rand(2, 16, 20, 3, device="cuda").permute(0, 3, 1, 2)
     assert_close(GaussianBlur(1.0).cuda()(xt), bo.gaussian_blur_torch_ref(xt.cpu().numpy(), 1.0), "permuted view")
+
+
+@pytest.mark.parametrize("std", [0.01, 0.5, 2.0, 5.0, 12.0, 23.0, 40.0])
+def test_tensor_core_path_matches_oracle_and_fma_path(std):
+    """128 x 128 planes run on tcgen05 (fp16 split, fp32 accumulate in TMEM): same 1e-5 bar, any input magnitude."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import blur_images
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(20, (7, 3, 128, 128))
+    x[1] *= 1e-6   # tiny plane magnitudes (gradients)
+    x[2] *= 3e4    # beyond fp16 range without the per-plane power-of-two scale
+    x[3, 0] = 0.0  # an all-zero plane
+    x[4, 1, 5:9, 100:] += 50.0
+    mod = GaussianBlur(std).cuda()
+    got = mod(_dev(x))
+    assert ops.last_blur_path() == 4
+    os.environ["BGAN_BLUR_NO_TC"] = "1"
+    try:
+        fma = mod(_dev(x))
+        assert ops.last_blur_path() in (1, 2)
+    finally:
+        os.environ.pop("BGAN_BLUR_NO_TC", None)
+    want = bo.gaussian_blur_torch_ref(x, std)
+    for n in range(x.shape[0]):  # per image: magnitudes differ by 10 orders
+        assert_close(got[n], want[n], "tensor-core path, image %d, std=%g" % (n, std))
+        assert_close(fma[n], want[n], "fma path, image %d, std=%g" % (n, std))
+    assert torch.count_nonzero(got[3, 0]).item() == 0
+    xt = uniform_pm1(21, (2, 3, 128, 128))
+    got_tf = blur_images(_dev(xt), std)
+    assert ops.last_blur_path() == 4
+    assert_close(got_tf, bo.blur_images_tf_ref(xt, std), "tensor-core path, tf rule, std=%g" % std)
