@@ -402,6 +402,11 @@ EncodeTiledFn encode_tiled_fn() {
 bool make_tmap(CUtensorMap* tm, const float* x, int planes, int H, int Wc, int box_w, int box_h) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
+    thread_local bool bound = false;  // the driver call needs a context bound to this thread (autograd worker threads)
+    if (!bound) {
+        cudaFree(nullptr);
+        bound = true;
+    }
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(Wc), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(planes)};
     const cuuint64_t strides[2] = {static_cast<cuuint64_t>(Wc) * 4, static_cast<cuuint64_t>(Wc) * H * 4};
     const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};

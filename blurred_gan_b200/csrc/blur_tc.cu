@@ -36,20 +36,24 @@ namespace bgan {
 namespace {
 
 constexpr int kP = 128;  // plane edge
-constexpr int kTcThreads = 256;
+// Two independent 256-thread streams per CTA, each with its own operand slot, barriers and TMEM half:
+// while one stream waits for its MMAs or its TMA load, the other runs its CUDA-core phases.
+constexpr int kStreamThreads = 256;
+constexpr int kStreams = 2;
+constexpr int kTcThreads = kStreamThreads * kStreams;
+constexpr int kF4PerThread = kP * kP / 4 / kStreamThreads;  // 16 float4 of the plane per thread
 // operand tile: K-major, no swizzle, core matrix = 8 rows x 16 bytes.  Core matrices adjacent in K are
 // 144 bytes apart (16 bytes of padding) so that a warp writing consecutive K-chunks of one row, or
 // consecutive rows of one chunk, never hits a bank twice.
 constexpr uint32_t kLBO = 144;              // K-adjacent core matrices
 constexpr uint32_t kSBO = 16 * kLBO;        // row-group (8 rows) stride = 2304
 constexpr uint32_t kTileBytes = 16 * kSBO;  // 36864
-constexpr uint32_t kOffStage = 0;           // fp32 plane, TMA destination (64 KB)
-constexpr uint32_t kOffT1 = 65536;
-constexpr uint32_t kOffT2 = kOffT1 + kTileBytes;
-constexpr uint32_t kOffO1 = kOffT2 + kTileBytes;  // X1, later Z1
-constexpr uint32_t kOffO2 = kOffO1 + kTileBytes;  // X2, later Z2
-constexpr uint32_t kOffMisc = kOffO2 + kTileBytes;
-constexpr uint32_t kSmemTc = kOffMisc + 1024 /* taps */ + 128;
+constexpr uint32_t kOffT1 = 0;
+constexpr uint32_t kOffT2 = kTileBytes;
+constexpr uint32_t kOffSlot = 2 * kTileBytes;   // per stream: [X1 | X2], later [Z1 | Z2]; also the TMA destination of the fp32 plane
+constexpr uint32_t kSlotBytes = 2 * kTileBytes; // 73728 >= 65536
+constexpr uint32_t kOffMisc = kOffSlot + kStreams * kSlotBytes;
+constexpr uint32_t kSmemTc = kOffMisc + 1024 /* taps */ + 256;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 // instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -98,20 +102,29 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// tcgen05.wait::ld with the destination registers as in/out operands, so that the compiler cannot move any use of
+// them above the wait
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                   "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]),
+                   "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]),
+                   "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane; the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+          "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+          "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // a -> (fp16(a), fp16((a - fp16(a)) * 2^11)) for two values at a time
@@ -135,28 +148,33 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a1, uint32_
     for (int k = 1; k < 8; ++k) umma_f16(d_tmem, da1 + k * kStep, db1 + k * kStep, 1);
 }
 
+__device__ __forceinline__ void stream_sync(int stream) {
+    asm volatile("bar.sync %0, %1;" ::"r"(stream + 1), "r"(kStreamThreads) : "memory");
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* stage = reinterpret_cast<float*>(smem + kOffStage);
     float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
-    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kOffMisc + 1024);
-    uint64_t* mbar_mma = mbar_tma + 1;
-    double* s_red = reinterpret_cast<double*>(mbar_tma + 2);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 3);
-    float* s_max = reinterpret_cast<float*>(mbar_tma + 4);  // 8 floats
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + kOffMisc + 1024);  // [tma0, tma1, mma0, mma1]
+    double* s_red = reinterpret_cast<double*>(mbars + 4);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbars + 5);
+    float* s_max_all = reinterpret_cast<float*>(mbars + 6);  // [stream][8]
     const uint32_t sbase = smem_u32(smem);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
+    const int stream = tid / kStreamThreads;
+    const int stid = tid % kStreamThreads;       // thread index inside the stream
+    const int swarp = stid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
-        mbar_init(mbar_tma, 1);
-        mbar_init(mbar_mma, 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mbar_init(mbars + i, 1);
         mbar_fence_init();
     }
     __syncwarp();
-    if (warp == 0) {  // 256 TMEM columns: D1 = [0, 128), D2 = [128, 256)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256) : "memory");
+    if (tid < 32) {  // 512 TMEM columns: per stream D1 = [0, 128), D2 = [128, 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // ---- T1, T2: banded Toeplitz operand tiles, built once per CTA -------------------------------------
@@ -176,39 +194,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc128_kernel(const TcArgs 
         *reinterpret_cast<uint4*>(smem + kOffT1 + off) = *reinterpret_cast<uint4*>(hi);
         *reinterpret_cast<uint4*>(smem + kOffT2 + off) = *reinterpret_cast<uint4*>(lo);
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const uint32_t d1 = tmem, d2 = tmem + 128;
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
-    const int col_half = (warp >> 2) * 64;
 
+    // ---- per-stream state ---------------------------------------------------------------------------------
+    unsigned char* slot = smem + kOffSlot + stream * kSlotBytes;
+    const uint32_t slot_s = sbase + kOffSlot + stream * kSlotBytes;
+    const float* stage = reinterpret_cast<const float*>(slot);
+    uint64_t* mbar_tma = mbars + stream;
+    uint64_t* mbar_mma = mbars + 2 + stream;
+    float* s_max = s_max_all + stream * 8;
+    const uint32_t tmem = *s_tmem + stream * 256;
+    const uint32_t d1 = tmem, d2 = tmem + 128;
+    const uint32_t lane_base = static_cast<uint32_t>((swarp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+    const int col_base = (swarp >> 2) * 64;
+    const int row = (swarp & 3) * 32 + lane;  // D row (= w') owned by this thread in the epilogues
+
+    const int first = stream * gridDim.x + blockIdx.x, stride = kStreams * gridDim.x;
     uint32_t par_tma = 0, par_mma = 0;
-    if (tid == 0 && blockIdx.x < a.planes) {
+    if (stid == 0 && first < a.planes) {
         mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-        tma_load_3d(stage, &tmap, mbar_tma, 0, 0, blockIdx.x);
+        tma_load_3d(slot, &tmap, mbar_tma, 0, 0, first);
     }
 
-    for (int p = blockIdx.x; p < a.planes; p += gridDim.x) {
-        // ---- fp32 plane -> registers, plane max ---------------------------------------------------------
+    for (int p = first; p < a.planes; p += stride) {
+        // ---- fp32 plane (landed in the slot) -> registers, plane max ---------------------------------------
         mbar_wait(mbar_tma, par_tma);
         par_tma ^= 1;
-        float4 v[16];
+        // the slot cannot take the next plane before this one's GEMM2 has finished: warm L2 with it meanwhile
+        if (stid == 0 && p + stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, p + stride);
+        float4 v[kF4PerThread];
         float m = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            v[j] = *reinterpret_cast<const float4*>(stage + (j * kTcThreads + tid) * 4);
+        for (int j = 0; j < kF4PerThread; ++j) {
+            v[j] = *reinterpret_cast<const float4*>(stage + (j * kStreamThreads + stid) * 4);
             m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) s_max[warp] = m;
-        __syncthreads();  // staging drained, s_max visible; the previous plane's GEMM2 has completed (waited in its epilogue)
-        if (tid == 0 && p + gridDim.x < a.planes) {
-            mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-            tma_load_3d(stage, &tmap, mbar_tma, 0, 0, p + gridDim.x);
-        }
+        if (lane == 0) s_max[swarp] = m;
+        stream_sync(stream);  // the whole plane is in registers: the slot may be overwritten with operand tiles
         m = s_max[0];
 #pragma unroll
         for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w]);
@@ -220,22 +247,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc128_kernel(const TcArgs 
 
         // ---- X1, X2 (B operand of GEMM1: row = h, K = w) ---------------------------------------------------
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = j * kTcThreads + tid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
+        for (int j = 0; j < kF4PerThread; ++j) {
+            const int f = j * kStreamThreads + stid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
             const int h = f >> 5, w = (f & 31) << 2;
             __half2 hi[2], lo[2];
             split2(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
             split2(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
             const uint32_t off = tile_off(h, w);
-            *reinterpret_cast<uint2*>(smem + kOffO1 + off) = *reinterpret_cast<uint2*>(hi);
-            *reinterpret_cast<uint2*>(smem + kOffO2 + off) = *reinterpret_cast<uint2*>(lo);
+            *reinterpret_cast<uint2*>(slot + off) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(slot + kTileBytes + off) = *reinterpret_cast<uint2*>(lo);
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        stream_sync(stream);
+        if (stid == 0) {
             tc_fence_after();
-            issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, sbase + kOffO1, sbase + kOffO2);  // D1 = T X^T
+            issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, slot_s, slot_s + kTileBytes);  // D1 = T X^T
             umma_commit(mbar_mma);
         }
         mbar_wait(mbar_mma, par_mma);
@@ -243,54 +270,76 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc128_kernel(const TcArgs 
         tc_fence_after();
 
         // ---- D1 -> Z1, Z2 (A operand of GEMM2: row = w', K = h); X tiles are dead once GEMM1 has completed -----
+        {
+            float z0[32], z1[32];
+            tmem_ld32_nowait(d1 + lane_base + col_base, z0);
+            tmem_ld32_nowait(d1 + lane_base + col_base + 32, z1);
+            tmem_ld_wait(z0);
+            tmem_ld_wait(z1);
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            float z[32];
-            const int h0 = col_half + cc * 32;
-            tmem_ld32(d1 + lane_base + h0, z);
-            const int row = (warp & 3) * 32 + lane;
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
+            for (int c8 = 0; c8 < 8; ++c8) {
                 __half2 hi[4], lo[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) split2(z[c8 * 8 + 2 * e], z[c8 * 8 + 2 * e + 1], hi[e], lo[e]);
-                const uint32_t off = tile_off(row, h0 + c8 * 8);
-                *reinterpret_cast<uint4*>(smem + kOffO1 + off) = *reinterpret_cast<uint4*>(hi);
-                *reinterpret_cast<uint4*>(smem + kOffO2 + off) = *reinterpret_cast<uint4*>(lo);
+                for (int e = 0; e < 4; ++e) {
+                    const float za = c8 < 4 ? z0[c8 * 8 + 2 * e] : z1[(c8 - 4) * 8 + 2 * e];
+                    const float zb = c8 < 4 ? z0[c8 * 8 + 2 * e + 1] : z1[(c8 - 4) * 8 + 2 * e + 1];
+                    split2(za, zb, hi[e], lo[e]);
+                }
+                const uint32_t off = tile_off(row, col_base + c8 * 8);
+                *reinterpret_cast<uint4*>(slot + off) = *reinterpret_cast<uint4*>(hi);
+                *reinterpret_cast<uint4*>(slot + kTileBytes + off) = *reinterpret_cast<uint4*>(lo);
             }
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        stream_sync(stream);
+        if (stid == 0) {
             tc_fence_after();
-            issue_gemm(d2, sbase + kOffO1, sbase + kOffO2, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
+            issue_gemm(d2, slot_s, slot_s + kTileBytes, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
             umma_commit(mbar_mma);
         }
         mbar_wait(mbar_mma, par_mma);
         par_mma ^= 1;
         tc_fence_after();
+        // the slot's tiles are dead: bring in the next plane while the epilogue drains TMEM
+        if (stid == 0 && p + stride < a.planes) {
+            mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+            tma_load_3d(slot, &tmap, mbar_tma, 0, 0, p + stride);
+        }
 
         // ---- D2 = Y^T -> global, coalesced along w' ---------------------------------------------------------
-        float* yp = a.y + static_cast<size_t>(p) * kP * kP + (warp & 3) * 32 + lane;
+        {
+            float* yp = a.y + static_cast<size_t>(p) * kP * kP + row;
+            float o0[32], o1[32];
+            tmem_ld32_nowait(d2 + lane_base + col_base, o0);
+            tmem_ld32_nowait(d2 + lane_base + col_base + 32, o1);
+            tmem_ld_wait(o0);
+            tmem_ld_wait(o1);
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            float o[32];
-            const int h0 = col_half + cc * 32;
-            tmem_ld32(d2 + lane_base + h0, o);
+            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o0[j] * inv_scale);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(h0 + j) * kP, o[j] * inv_scale);
+            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + 32 + j) * kP, o1[j] * inv_scale);
         }
         tc_fence_before();
     }
 
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"(512) : "memory");
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled is a driver entry point and needs a context bound to the calling thread; PyTorch's autograd
+// worker threads only have the runtime's lazy binding, so force it once per thread.
+void bind_primary_context() {
+    thread_local bool bound = false;
+    if (!bound) {
+        cudaFree(nullptr);
+        bound = true;
+    }
+}
 
 EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = [] {
@@ -318,6 +367,7 @@ bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, c
 int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff, int radius, cudaStream_t stream) {
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
+    bind_primary_context();
     const cuuint64_t dims[3] = {kP, kP, static_cast<cuuint64_t>(planes)};
     const cuuint64_t strides[2] = {kP * 4, kP * kP * 4};
     const cuuint32_t box[3] = {kP, kP, 1};
@@ -334,7 +384,7 @@ int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff
         attr_dev = dev;
     }
     TcArgs a{y, planes, rule, std_eff, radius};
-    const unsigned grid = static_cast<unsigned>(std::min(planes, device_sm_count()));
+    const unsigned grid = static_cast<unsigned>(std::min((planes + kStreams - 1) / kStreams, device_sm_count()));
     blur_tc128_kernel<<<grid, kTcThreads, kSmemTc, stream>>>(a, tmap);
     BGAN_LAUNCH_OK();
     return 0;
