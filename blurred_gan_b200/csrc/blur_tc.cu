@@ -36,29 +36,31 @@ namespace bgan {
 namespace {
 
 constexpr int kP = 128;  // plane edge
-// Two independent 256-thread streams per CTA, each with its own operand slot, barriers and TMEM half:
-// while one stream waits for its MMAs or its TMA load, the other runs its CUDA-core phases.
-constexpr int kStreamThreads = 256;
-constexpr int kStreams = 2;
-constexpr int kTcThreads = kStreamThreads * kStreams;
-constexpr int kF4PerThread = kP * kP / 4 / kStreamThreads;  // 16 float4 of the plane per thread
+constexpr int kTcThreads = 512;                          // compute threads; one more warp only issues the MMAs
+constexpr int kTcWarps = kTcThreads / 32;                // 16: TMEM lane quadrant = warp & 3, column group = warp >> 2
+constexpr int kMmaWarp = kTcWarps;
+constexpr int kCtaThreads = kTcThreads + 32;
+constexpr int kColsPerWarp = kP / (kTcWarps / 4);        // 32 accumulator columns per thread in the epilogues
+constexpr int kF4PerThread = kP * kP / 4 / kTcThreads;   // 8 float4 of the plane per thread
 // operand tile: K-major, no swizzle, core matrix = 8 rows x 16 bytes.  Core matrices adjacent in K are
 // 144 bytes apart (16 bytes of padding) so that a warp writing consecutive K-chunks of one row, or
 // consecutive rows of one chunk, never hits a bank twice.
 constexpr uint32_t kLBO = 144;              // K-adjacent core matrices
 constexpr uint32_t kSBO = 16 * kLBO;        // row-group (8 rows) stride = 2304
 constexpr uint32_t kTileBytes = 16 * kSBO;  // 36864
-constexpr uint32_t kOffT1 = 0;
-constexpr uint32_t kOffT2 = kTileBytes;
-constexpr uint32_t kOffSlot = 2 * kTileBytes;   // per stream: [X1 | X2], later [Z1 | Z2]; also the TMA destination of the fp32 plane
-constexpr uint32_t kSlotBytes = 2 * kTileBytes; // 73728 >= 65536
-constexpr uint32_t kOffMisc = kOffSlot + kStreams * kSlotBytes;
+constexpr uint32_t kOffStage = 0;           // fp32 plane, TMA destination (64 KB)
+constexpr uint32_t kOffT1 = 65536;
+constexpr uint32_t kOffT2 = kOffT1 + kTileBytes;
+constexpr uint32_t kOffO1 = kOffT2 + kTileBytes;  // X1, later Z1
+constexpr uint32_t kOffO2 = kOffO1 + kTileBytes;  // X2, later Z2
+constexpr uint32_t kOffMisc = kOffO2 + kTileBytes;
 constexpr uint32_t kSmemTc = kOffMisc + 1024 /* taps */ + 256;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 // instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct TcArgs {
+    long long* trace;  // debug: clock64 stamps of CTA 0 / thread 0 (nullptr in production)
     float* y;
     int planes;
     int rule;
@@ -96,6 +98,37 @@ __device__ __forceinline__ void umma_f16_scale_d11(uint32_t d_tmem, uint64_t ade
         "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
 }
+// A operand from TMEM (fp16, two K-elements per 32-bit column, lane = row), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(kIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_scale_d11(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p, 11;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(kIdesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -148,38 +181,66 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a1, uint32_
     for (int k = 1; k < 8; ++k) umma_f16(d_tmem, da1 + k * kStep, db1 + k * kStep, 1);
 }
 
-__device__ __forceinline__ void stream_sync(int stream) {
-    asm volatile("bar.sync %0, %1;" ::"r"(stream + 1), "r"(kStreamThreads) : "memory");
+// Software pipeline of one CTA over its planes p0, p1, ... (all 512 threads take part in every CUDA-core phase,
+// thread 0 issues the MMAs, which run asynchronously):
+//
+//   convert(p): registers -> X tiles      | issue GEMM1(p)
+//   store(p-1): D2[prev] -> global        |   ... GEMM1(p) running on the tensor pipe
+//   wait GEMM1(p); split(p): D1 -> Z tiles| issue GEMM2(p)
+//   fetch(p+1): staging -> registers, max |   ... GEMM2(p) running; then TMA(p+2) -> staging
+//   wait GEMM2(p)
+//
+// so the global store of the previous plane and the staging read of the next one hide behind the two GEMMs,
+// and the TMA load of plane p+2 has a whole iteration to land.
+// GEMM2 with the A operand (Z^T split into hi | lo, 64 + 64 columns at z_tmem) read from TMEM
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t z_tmem, uint32_t b1, uint32_t b2) {
+    const uint64_t db1 = smem_desc(b1), db2 = smem_desc(b2);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+    const uint32_t a1 = z_tmem, a2 = z_tmem + 64;  // 8 columns per K = 16
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_f16_ts(d_tmem, a1 + 8 * k, db2 + k * kStep, k > 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_f16_ts(d_tmem, a2 + 8 * k, db1 + k * kStep, 1);
+    umma_f16_ts_scale_d11(d_tmem, a1, db1);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) umma_f16_ts(d_tmem, a1 + 8 * k, db1 + k * kStep, 1);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
     float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
-    uint64_t* mbars = reinterpret_cast<uint64_t*>(smem + kOffMisc + 1024);  // [tma0, tma1, mma0, mma1]
-    double* s_red = reinterpret_cast<double*>(mbars + 4);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbars + 5);
-    float* s_max_all = reinterpret_cast<float*>(mbars + 6);  // [stream][8]
+    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kOffMisc + 1024);
+    uint64_t* mbar_mma = mbar_tma + 1;
+    double* s_red = reinterpret_cast<double*>(mbar_tma + 2);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 3);
+    float* s_max = reinterpret_cast<float*>(mbar_tma + 4);  // [2][16]
     const uint32_t sbase = smem_u32(smem);
 
-    const int tid = threadIdx.x;
-    const int stream = tid / kStreamThreads;
-    const int stid = tid % kStreamThreads;       // thread index inside the stream
-    const int swarp = stid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 127) a.trace[1 + n_stamp++] = clock64();
+    };
+    stamp();  // 0: kernel start
 
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mbar_init(mbars + i, 1);
+        mbar_init(mbar_tma, 1);
+        mbar_init(mbar_mma, 1);
         mbar_fence_init();
+        // the first plane starts moving before anything else is set up
+        mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+        tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, blockIdx.x);
     }
     __syncwarp();
-    if (tid < 32) {  // 512 TMEM columns: per stream D1 = [0, 128), D2 = [128, 256)
+    if (warp == 0) {  // TMEM columns: D1 = [0, 128), Z^T as fp16 hi | lo = [128, 256), D2 double-buffered = [256, 384) / [384, 512)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // ---- T1, T2: banded Toeplitz operand tiles, built once per CTA -------------------------------------
     normalised_taps(a.rule, a.std_eff, a.radius, nullptr, s_g, s_red);  // syncs inside
-    for (int idx = tid; idx < kP * 16; idx += kTcThreads) {
+    for (int idx = tid; idx < kP * 16; idx += kCtaThreads) {
         const int row = idx & 127, chunk = idx >> 7;  // lanes <-> consecutive rows: conflict-free 16-byte stores
         __half2 hi[4], lo[4];
 #pragma unroll
@@ -198,133 +259,163 @@ __global__ void __launch_bounds__(kTcThreads, 1) blur_tc128_kernel(const TcArgs 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t d1 = tmem;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+    const int col_base = (warp >> 2) * kColsPerWarp;
+    const int row = (warp & 3) * 32 + lane;  // accumulator row (= w') owned by this thread in the epilogues
 
-    // ---- per-stream state ---------------------------------------------------------------------------------
-    unsigned char* slot = smem + kOffSlot + stream * kSlotBytes;
-    const uint32_t slot_s = sbase + kOffSlot + stream * kSlotBytes;
-    const float* stage = reinterpret_cast<const float*>(slot);
-    uint64_t* mbar_tma = mbars + stream;
-    uint64_t* mbar_mma = mbars + 2 + stream;
-    float* s_max = s_max_all + stream * 8;
-    const uint32_t tmem = *s_tmem + stream * 256;
-    const uint32_t d1 = tmem, d2 = tmem + 128;
-    const uint32_t lane_base = static_cast<uint32_t>((swarp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
-    const int col_base = (swarp >> 2) * 64;
-    const int row = (swarp & 3) * 32 + lane;  // D row (= w') owned by this thread in the epilogues
-
-    const int first = stream * gridDim.x + blockIdx.x, stride = kStreams * gridDim.x;
+    const int first = blockIdx.x, stride = gridDim.x;
+    stamp();  // 1: prologue (TMEM, taps, T tiles) done
     uint32_t par_tma = 0, par_mma = 0;
-    if (stid == 0 && first < a.planes) {
-        mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-        tma_load_3d(slot, &tmap, mbar_tma, 0, 0, first);
-    }
+    float4 v[kF4PerThread];
 
-    for (int p = first; p < a.planes; p += stride) {
-        // ---- fp32 plane (landed in the slot) -> registers, plane max ---------------------------------------
+    // staging -> registers + per-warp max into s_max[buf]; ends with a CTA barrier, after which staging is free
+    auto fetch = [&](int buf) {
         mbar_wait(mbar_tma, par_tma);
         par_tma ^= 1;
-        // the slot cannot take the next plane before this one's GEMM2 has finished: warm L2 with it meanwhile
-        if (stid == 0 && p + stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, p + stride);
-        float4 v[kF4PerThread];
         float m = 0.0f;
 #pragma unroll
         for (int j = 0; j < kF4PerThread; ++j) {
-            v[j] = *reinterpret_cast<const float4*>(stage + (j * kStreamThreads + stid) * 4);
+            v[j] = *reinterpret_cast<const float4*>(stage + (j * kTcThreads + tid) * 4);
             m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) s_max[swarp] = m;
-        stream_sync(stream);  // the whole plane is in registers: the slot may be overwritten with operand tiles
-        m = s_max[0];
+        if (lane == 0) s_max[buf * kTcWarps + warp] = m;
+        __syncthreads();
+    };
+    auto load_plane = [&](int plane) {
+        mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+        tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, plane);
+    };
+
+    if (warp == kMmaWarp) {
+        // ---- MMA issuer: mirrors the CTA barriers of the compute warps and does nothing else -----------------
+        __syncthreads();  // fetch(0)
+        int it = 0;
+        for (int p = first; p < a.planes; p += stride, ++it) {
+            __syncthreads();  // X tiles written
+            if (lane == 0) {
+                tc_fence_after();
+                issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, sbase + kOffO1, sbase + kOffO2);  // D1 = T X^T
+                umma_commit(mbar_mma);
+            }
+            __syncwarp();
+            __syncthreads();  // Z tiles written
+            if (lane == 0) {
+                tc_fence_after();
+                issue_gemm_ts(tmem + 256 + (it & 1) * 128, tmem + 128, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T
+                umma_commit(mbar_mma);
+            }
+            __syncwarp();
+            if (p + stride < a.planes) __syncthreads();  // fetch(next)
+        }
+        __syncthreads();
+        return;
+    }
+
+    fetch(0);
+    if (tid == 0 && first + stride < a.planes) load_plane(first + stride);
+    stamp();  // 2: first plane in registers
+
+    float inv_prev = 0.0f;
+    int it = 0;
+    for (int p = first; p < a.planes; p += stride, ++it) {
+        // ---- scale of this plane: power of two putting max|x| in [2^12, 2^13) ------------------------------
+        float m = s_max[(it & 1) * kTcWarps];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w]);
-        // power-of-two scale putting max|x| in [2^12, 2^13)
+        for (int w = 1; w < kTcWarps; ++w) m = fmaxf(m, s_max[(it & 1) * kTcWarps + w]);
         int eb = (__float_as_int(m) >> 23) & 0xff;
         eb = min(max(eb, 13), 254);
         const float scale = __int_as_float((266 - eb) << 23);
         const float inv_scale = __int_as_float((eb - 12) << 23);
 
-        // ---- X1, X2 (B operand of GEMM1: row = h, K = w) ---------------------------------------------------
+        // ---- convert: X1, X2 (B operand of GEMM1: row = h, K = w) ------------------------------------------
 #pragma unroll
         for (int j = 0; j < kF4PerThread; ++j) {
-            const int f = j * kStreamThreads + stid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
+            const int f = j * kTcThreads + tid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
             const int h = f >> 5, w = (f & 31) << 2;
             __half2 hi[2], lo[2];
             split2(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
             split2(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
             const uint32_t off = tile_off(h, w);
-            *reinterpret_cast<uint2*>(slot + off) = *reinterpret_cast<uint2*>(hi);
-            *reinterpret_cast<uint2*>(slot + kTileBytes + off) = *reinterpret_cast<uint2*>(lo);
+            *reinterpret_cast<uint2*>(smem + kOffO1 + off) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(smem + kOffO2 + off) = *reinterpret_cast<uint2*>(lo);
         }
+        stamp();  // +0: convert done (this thread)
         fence_proxy_async();
         tc_fence_before();
-        stream_sync(stream);
-        if (stid == 0) {
-            tc_fence_after();
-            issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, slot_s, slot_s + kTileBytes);  // D1 = T X^T
-            umma_commit(mbar_mma);
+        __syncthreads();  // -> the MMA warp issues GEMM1(p)
+        stamp();  // +1: barrier passed
+
+        // ---- store(p - stride): D2[prev] = Y^T -> global, coalesced along w'; hides behind GEMM1(p) -----------
+        if (it > 0) {
+            float* yp = a.y + static_cast<size_t>(p - stride) * kP * kP + row;
+            float o[32];
+            tmem_ld32_nowait(tmem + 256 + ((it - 1) & 1) * 128 + lane_base + col_base, o);
+            tmem_ld_wait(o);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o[j] * inv_prev);
         }
+        inv_prev = inv_scale;
+        stamp();  // +3: store(prev) done
+
         mbar_wait(mbar_mma, par_mma);
         par_mma ^= 1;
         tc_fence_after();
+        stamp();  // +4: GEMM1 complete
 
-        // ---- D1 -> Z1, Z2 (A operand of GEMM2: row = w', K = h); X tiles are dead once GEMM1 has completed -----
+        // ---- split: D1 (fp32) -> Z^T hi | lo as packed fp16 back into TMEM (A operand of GEMM2: lane = w', K = h) ----
         {
-            float z0[32], z1[32];
-            tmem_ld32_nowait(d1 + lane_base + col_base, z0);
-            tmem_ld32_nowait(d1 + lane_base + col_base + 32, z1);
-            tmem_ld_wait(z0);
-            tmem_ld_wait(z1);
+            float z[32];
+            tmem_ld32_nowait(d1 + lane_base + col_base, z);
+            tmem_ld_wait(z);
+            uint32_t zh[16], zl[16];
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                __half2 hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float za = c8 < 4 ? z0[c8 * 8 + 2 * e] : z1[(c8 - 4) * 8 + 2 * e];
-                    const float zb = c8 < 4 ? z0[c8 * 8 + 2 * e + 1] : z1[(c8 - 4) * 8 + 2 * e + 1];
-                    split2(za, zb, hi[e], lo[e]);
-                }
-                const uint32_t off = tile_off(row, col_base + c8 * 8);
-                *reinterpret_cast<uint4*>(slot + off) = *reinterpret_cast<uint4*>(hi);
-                *reinterpret_cast<uint4*>(slot + kTileBytes + off) = *reinterpret_cast<uint4*>(lo);
+            for (int e = 0; e < 16; ++e) {
+                __half2 hi, lo;
+                split2(z[2 * e], z[2 * e + 1], hi, lo);
+                zh[e] = *reinterpret_cast<uint32_t*>(&hi);
+                zl[e] = *reinterpret_cast<uint32_t*>(&lo);
             }
+            tmem_st16(tmem + 128 + lane_base + (col_base >> 1), zh);
+            tmem_st16(tmem + 128 + 64 + lane_base + (col_base >> 1), zl);
+            tmem_st_wait();
         }
+        stamp();  // +5: split done (this thread)
         fence_proxy_async();
         tc_fence_before();
-        stream_sync(stream);
-        if (stid == 0) {
-            tc_fence_after();
-            issue_gemm(d2, slot_s, slot_s + kTileBytes, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
-            umma_commit(mbar_mma);
+        __syncthreads();  // -> the MMA warp issues GEMM2(p)
+        stamp();  // +6: barrier passed
+
+        // ---- fetch(p + stride) behind GEMM2(p), then start the TMA load of p + 2 stride ------------------------
+        if (p + stride < a.planes) {
+            fetch((it + 1) & 1);
+            if (tid == 0 && p + 2 * stride < a.planes) load_plane(p + 2 * stride);
         }
+        stamp();  // +7: fetch(next) done
+
         mbar_wait(mbar_mma, par_mma);
         par_mma ^= 1;
         tc_fence_after();
-        // the slot's tiles are dead: bring in the next plane while the epilogue drains TMEM
-        if (stid == 0 && p + stride < a.planes) {
-            mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-            tma_load_3d(slot, &tmap, mbar_tma, 0, 0, p + stride);
-        }
-
-        // ---- D2 = Y^T -> global, coalesced along w' ---------------------------------------------------------
-        {
-            float* yp = a.y + static_cast<size_t>(p) * kP * kP + row;
-            float o0[32], o1[32];
-            tmem_ld32_nowait(d2 + lane_base + col_base, o0);
-            tmem_ld32_nowait(d2 + lane_base + col_base + 32, o1);
-            tmem_ld_wait(o0);
-            tmem_ld_wait(o1);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o0[j] * inv_scale);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + 32 + j) * kP, o1[j] * inv_scale);
-        }
-        tc_fence_before();
+        stamp();  // +8: GEMM2 complete
     }
-
+    // ---- drain: the last plane's D2 --------------------------------------------------------------------------
+    {
+        const int p_last = first + (it - 1) * stride;
+        float* yp = a.y + static_cast<size_t>(p_last) * kP * kP + row;
+        float o[32];
+        tmem_ld32_nowait(tmem + 256 + ((it - 1) & 1) * 128 + lane_base + col_base, o);
+        tmem_ld_wait(o);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o[j] * inv_prev);
+    }
+    stamp();  // drain done
+    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) a.trace[0] = n_stamp;
+    tc_fence_before();
     __syncthreads();
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"(512) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -383,9 +474,10 @@ int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff
         BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
         attr_dev = dev;
     }
-    TcArgs a{y, planes, rule, std_eff, radius};
-    const unsigned grid = static_cast<unsigned>(std::min((planes + kStreams - 1) / kStreams, device_sm_count()));
-    blur_tc128_kernel<<<grid, kTcThreads, kSmemTc, stream>>>(a, tmap);
+    const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
+    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, y, planes, rule, std_eff, radius};
+    const unsigned grid = static_cast<unsigned>(std::min(planes, device_sm_count()));
+    blur_tc128_kernel<<<grid, kCtaThreads, kSmemTc, stream>>>(a, tmap);
     BGAN_LAUNCH_OK();
     return 0;
 }
