@@ -38,8 +38,10 @@ namespace {
 constexpr int kP = 128;  // plane edge
 constexpr int kTcThreads = 512;                          // compute threads; one more warp only issues the MMAs
 constexpr int kTcWarps = kTcThreads / 32;                // 16: TMEM lane quadrant = warp & 3, column group = warp >> 2
-constexpr int kMmaWarp = kTcWarps;
-constexpr int kCtaThreads = kTcThreads + 32;
+constexpr int kMmaWarp = kTcWarps;                       // warp 16 issues the MMAs
+constexpr int kStoreWarp0 = kTcWarps + 1;                // warps 17..20 drain D2 to global memory
+constexpr int kStoreWarps = 4;
+constexpr int kCtaThreads = kTcThreads + 32 + 32 * kStoreWarps;  // 672
 constexpr int kColsPerWarp = kP / (kTcWarps / 4);        // 32 accumulator columns per thread in the epilogues
 constexpr int kF4PerThread = kP * kP / 4 / kTcThreads;   // 8 float4 of the plane per thread
 // operand tile: K-major, no swizzle, core matrix = 8 rows x 16 bytes.  Core matrices adjacent in K are
@@ -181,17 +183,6 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a1, uint32_
     for (int k = 1; k < 8; ++k) umma_f16(d_tmem, da1 + k * kStep, db1 + k * kStep, 1);
 }
 
-// Software pipeline of one CTA over its planes p0, p1, ... (all 512 threads take part in every CUDA-core phase,
-// thread 0 issues the MMAs, which run asynchronously):
-//
-//   convert(p): registers -> X tiles      | issue GEMM1(p)
-//   store(p-1): D2[prev] -> global        |   ... GEMM1(p) running on the tensor pipe
-//   wait GEMM1(p); split(p): D1 -> Z tiles| issue GEMM2(p)
-//   fetch(p+1): staging -> registers, max |   ... GEMM2(p) running; then TMA(p+2) -> staging
-//   wait GEMM2(p)
-//
-// so the global store of the previous plane and the staging read of the next one hide behind the two GEMMs,
-// and the TMA load of plane p+2 has a whole iteration to land.
 // GEMM2 with the A operand (Z^T split into hi | lo, 64 + 64 columns at z_tmem) read from TMEM
 __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t z_tmem, uint32_t b1, uint32_t b2) {
     const uint64_t db1 = smem_desc(b1), db2 = smem_desc(b2);
@@ -206,30 +197,54 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t z_tmem, 
     for (int k = 1; k < 8; ++k) umma_f16_ts(d_tmem, a1 + 8 * k, db1 + k * kStep, 1);
 }
 
+// Warp-specialised software pipeline of one CTA over its planes p0, p1, ... :
+//
+//   compute warps 0-15          MMA warp 16                     store warps 17-20
+//   ------------------------    ----------------------------    ---------------------------------
+//   [X(p) tiles ready] -------> GEMM1(p): D1 = T X^T
+//   fetch(p+1): staging->regs
+//   wait GEMM1(p)
+//   split(p): D1 -> Z (TMEM) -> GEMM2(p): D2[p&1] = Z^T T  --->  wait GEMM2(p); D2[p&1] -> global
+//   convert(p+1): regs -> X tiles (free since GEMM1(p) completed); overlaps GEMM2(p)
+//
+// The tensor pipe only idles during split; the global store, the staging read and the fp16 conversion of the
+// next plane all hide behind the MMAs, and the TMA load of plane p+2 has a whole iteration to land.
 __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
     float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
     uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kOffMisc + 1024);
-    uint64_t* mbar_mma = mbar_tma + 1;
-    double* s_red = reinterpret_cast<double*>(mbar_tma + 2);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 3);
-    float* s_max = reinterpret_cast<float*>(mbar_tma + 4);  // [2][16]
+    uint64_t* mbar_g1 = mbar_tma + 1;
+    uint64_t* mbar_g2 = mbar_tma + 2;      // [2]: GEMM2 into D2[b] complete
+    uint64_t* mbar_d2free = mbar_tma + 4;  // [2]: D2[b] has been read out
+    double* s_red = reinterpret_cast<double*>(mbar_tma + 6);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 7);
+    float* s_inv = reinterpret_cast<float*>(mbar_tma + 8);   // [4] ring: 1 / scale of plane it
+    float* s_max = s_inv + 4;                                // [2][16]
     const uint32_t sbase = smem_u32(smem);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int n_stamp = 0;
     auto stamp = [&]() {
-        if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 127) a.trace[1 + n_stamp++] = clock64();
+        if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 120) a.trace[1 + n_stamp++] = clock64();
     };
+    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) a.trace[126] = static_cast<long long>(global_timer_ns());
     stamp();  // 0: kernel start
 
+    // Programmatic dependent launch: the next kernel in the stream may start its own prologue as soon as our CTAs
+    // retire; we, in turn, must not read global memory before the previous grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
         mbar_init(mbar_tma, 1);
-        mbar_init(mbar_mma, 1);
+        mbar_init(mbar_g1, 1);
+        mbar_init(mbar_g2 + 0, 1);
+        mbar_init(mbar_g2 + 1, 1);
+        mbar_init(mbar_d2free + 0, kStoreWarps);
+        mbar_init(mbar_d2free + 1, kStoreWarps);
         mbar_fence_init();
-        // the first plane starts moving before anything else is set up
+        // the first plane starts moving before anything else is set up (but not before the producer of x is done)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
         tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, blockIdx.x);
     }
@@ -238,181 +253,212 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ---- T1, T2: banded Toeplitz operand tiles, built once per CTA -------------------------------------
-    normalised_taps(a.rule, a.std_eff, a.radius, nullptr, s_g, s_red);  // syncs inside
-    for (int idx = tid; idx < kP * 16; idx += kCtaThreads) {
-        const int row = idx & 127, chunk = idx >> 7;  // lanes <-> consecutive rows: conflict-free 16-byte stores
-        __half2 hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k0 = chunk * 8 + 2 * e;
-            const int d0 = k0 - row + a.radius, d1 = d0 + 1;
-            const float t0 = (d0 >= 0 && d0 <= 2 * a.radius) ? s_g[d0] : 0.0f;
-            const float t1 = (d1 >= 0 && d1 <= 2 * a.radius) ? s_g[d1] : 0.0f;
-            split2(t0, t1, hi[e], lo[e]);
+    stamp();  // after barrier init / TMEM alloc (warp 0)
+    // ---- taps: one warp, reference expression order ---------------------------------------------------------
+    const int n_taps = 2 * a.radius + 1;
+    if (warp == 1) {
+        float part = 0.0f;
+        for (int t = lane; t < n_taps; t += 32) {
+            const float g = raw_tap(a.rule, a.std_eff, t - a.radius);
+            s_g[t] = g;
+            part += g;
         }
-        const uint32_t off = tile_off(row, chunk * 8);
-        *reinterpret_cast<uint4*>(smem + kOffT1 + off) = *reinterpret_cast<uint4*>(hi);
-        *reinterpret_cast<uint4*>(smem + kOffT2 + off) = *reinterpret_cast<uint4*>(lo);
+        // fp32 partial sums of <= 8 taps each, combined in fp64: within 1 ulp of the reference's fp32 sum
+        const float tot = static_cast<float>(warp_sum(static_cast<double>(part)));
+        __syncwarp();
+        for (int t = lane; t < n_taps; t += 32) s_g[t] = s_g[t] / tot;
     }
+    __syncthreads();
+    stamp();  // taps ready
+    // ---- chunk table: a 16-byte chunk of T (row, K = 8c .. 8c+7) holds taps d0 .. d0+7 with d0 = 8c - row + r, so there
+    // are only n_taps + 7 distinct non-zero chunks.  Build them once (fp16 hi | lo), then T1 / T2 are plain copies. ----
+    uint4* s_chi = reinterpret_cast<uint4*>(smem + kOffO1);  // scratch inside the (not yet used) X tiles
+    uint4* s_clo = s_chi + 272;
+    for (int j = tid; j < (n_taps + 7) * 4; j += kCtaThreads) {
+        const int i = j >> 2, e = j & 3;
+        const int da = i - 7 + 2 * e, db = da + 1;
+        __half2 hi, lo;
+        split2((da >= 0 && da < n_taps) ? s_g[da] : 0.0f, (db >= 0 && db < n_taps) ? s_g[db] : 0.0f, hi, lo);
+        reinterpret_cast<__half2*>(s_chi + i)[e] = hi;
+        reinterpret_cast<__half2*>(s_clo + i)[e] = lo;
+    }
+    __syncthreads();
+    stamp();  // chunk table
+    for (int idx = tid; idx < kP * 16; idx += kCtaThreads) {
+        const int row = idx & 127, chunk = idx >> 7;  // lanes <-> consecutive rows: conflict-free 16-byte loads and stores
+        const int i = chunk * 8 - row + a.radius + 7;
+        const bool band = i >= 0 && i < n_taps + 7;
+        const uint32_t off = tile_off(row, chunk * 8);
+        *reinterpret_cast<uint4*>(smem + kOffT1 + off) = band ? s_chi[i] : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(smem + kOffT2 + off) = band ? s_clo[i] : make_uint4(0, 0, 0, 0);
+    }
+    stamp();  // T copied
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t d1 = tmem;
+    const uint32_t d1 = tmem, zp = tmem + 128, d2 = tmem + 256;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
-    const int col_base = (warp >> 2) * kColsPerWarp;
-    const int row = (warp & 3) * 32 + lane;  // accumulator row (= w') owned by this thread in the epilogues
-
+    const int row = (warp & 3) * 32 + lane;  // accumulator row (= w') owned by this thread
     const int first = blockIdx.x, stride = gridDim.x;
     stamp();  // 1: prologue (TMEM, taps, T tiles) done
-    uint32_t par_tma = 0, par_mma = 0;
-    float4 v[kF4PerThread];
-
-    // staging -> registers + per-warp max into s_max[buf]; ends with a CTA barrier, after which staging is free
-    auto fetch = [&](int buf) {
-        mbar_wait(mbar_tma, par_tma);
-        par_tma ^= 1;
-        float m = 0.0f;
-#pragma unroll
-        for (int j = 0; j < kF4PerThread; ++j) {
-            v[j] = *reinterpret_cast<const float4*>(stage + (j * kTcThreads + tid) * 4);
-            m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) s_max[buf * kTcWarps + warp] = m;
-        __syncthreads();
-    };
-    auto load_plane = [&](int plane) {
-        mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-        tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, plane);
-    };
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // (all threads: y may still be read by the previous grid)
 
     if (warp == kMmaWarp) {
-        // ---- MMA issuer: mirrors the CTA barriers of the compute warps and does nothing else -----------------
-        __syncthreads();  // fetch(0)
+        // ================= MMA issuer =================================================================
         int it = 0;
         for (int p = first; p < a.planes; p += stride, ++it) {
-            __syncthreads();  // X tiles written
+            named_bar_sync(1, kTcThreads + 32);  // X(p) tiles written
             if (lane == 0) {
                 tc_fence_after();
                 issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, sbase + kOffO1, sbase + kOffO2);  // D1 = T X^T
-                umma_commit(mbar_mma);
+                umma_commit(mbar_g1);
             }
             __syncwarp();
-            __syncthreads();  // Z tiles written
+            named_bar_sync(1, kTcThreads + 32);  // Z(p) written to TMEM
             if (lane == 0) {
+                if (it >= 2) mbar_wait(mbar_d2free + (it & 1), ((it - 2) >> 1) & 1);  // D2[it & 1] drained by the store warps
                 tc_fence_after();
-                issue_gemm_ts(tmem + 256 + (it & 1) * 128, tmem + 128, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T
-                umma_commit(mbar_mma);
+                issue_gemm_ts(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
+                umma_commit(mbar_g2 + (it & 1));
             }
             __syncwarp();
-            if (p + stride < a.planes) __syncthreads();  // fetch(next)
         }
-        __syncthreads();
-        return;
-    }
-
-    fetch(0);
-    if (tid == 0 && first + stride < a.planes) load_plane(first + stride);
-    stamp();  // 2: first plane in registers
-
-    float inv_prev = 0.0f;
-    int it = 0;
-    for (int p = first; p < a.planes; p += stride, ++it) {
-        // ---- scale of this plane: power of two putting max|x| in [2^12, 2^13) ------------------------------
-        float m = s_max[(it & 1) * kTcWarps];
+    } else if (warp >= kStoreWarp0) {
+        // ================= store warps: D2 = Y^T -> global, coalesced along w' =================================
+        int it = 0;
+        for (int p = first; p + stride < a.planes; p += stride, ++it) {  // (the last plane is drained by the compute warps)
+            mbar_wait(mbar_g2 + (it & 1), (it >> 1) & 1);
+            tc_fence_after();
+            const float inv = s_inv[it & 3];
+            float* yp = a.y + static_cast<size_t>(p) * kP * kP + row;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float o[32];
+                tmem_ld32_nowait(d2 + (it & 1) * 128 + lane_base + c * 32, o);
+                tmem_ld_wait(o);
+                if (c == 3) {  // everything of D2[it & 1] is in registers: hand the buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(mbar_d2free + (it & 1));
+                }
 #pragma unroll
-        for (int w = 1; w < kTcWarps; ++w) m = fmaxf(m, s_max[(it & 1) * kTcWarps + w]);
-        int eb = (__float_as_int(m) >> 23) & 0xff;
-        eb = min(max(eb, 13), 254);
-        const float scale = __int_as_float((266 - eb) << 23);
-        const float inv_scale = __int_as_float((eb - 12) << 23);
-
-        // ---- convert: X1, X2 (B operand of GEMM1: row = h, K = w) ------------------------------------------
-#pragma unroll
-        for (int j = 0; j < kF4PerThread; ++j) {
-            const int f = j * kTcThreads + tid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
-            const int h = f >> 5, w = (f & 31) << 2;
-            __half2 hi[2], lo[2];
-            split2(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
-            split2(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
-            const uint32_t off = tile_off(h, w);
-            *reinterpret_cast<uint2*>(smem + kOffO1 + off) = *reinterpret_cast<uint2*>(hi);
-            *reinterpret_cast<uint2*>(smem + kOffO2 + off) = *reinterpret_cast<uint2*>(lo);
+                for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(c * 32 + j) * kP, o[j] * inv);
+            }
         }
-        stamp();  // +0: convert done (this thread)
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();  // -> the MMA warp issues GEMM1(p)
-        stamp();  // +1: barrier passed
+    } else {
+        // ================= compute warps ==============================================================
+        const int col_base = (warp >> 2) * kColsPerWarp;
+        uint32_t par_tma = 0;
+        float4 v[kF4PerThread];
 
-        // ---- store(p - stride): D2[prev] = Y^T -> global, coalesced along w'; hides behind GEMM1(p) -----------
-        if (it > 0) {
-            float* yp = a.y + static_cast<size_t>(p - stride) * kP * kP + row;
+        // staging -> registers + per-warp max into s_max[buf]; ends with a barrier of the compute warps, after which
+        // staging is free and thread 0 starts the TMA load of the plane after next
+        auto fetch = [&](int buf, int next_plane) {
+            mbar_wait(mbar_tma, par_tma);
+            par_tma ^= 1;
+            float m = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kF4PerThread; ++j) {
+                v[j] = *reinterpret_cast<const float4*>(stage + (j * kTcThreads + tid) * 4);
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) s_max[buf * kTcWarps + warp] = m;
+            named_bar_sync(2, kTcThreads);
+            if (tid == 0 && next_plane < a.planes) {
+                mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+                tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, next_plane);
+                if (next_plane + stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, next_plane + stride);  // warm L2 one more ahead
+            }
+        };
+        // registers -> X1, X2 tiles (B operand of GEMM1: row = h, K = w), scaled so that max|x| is in [2^12, 2^13)
+        auto convert = [&](int buf, int it_of_plane) {
+            float m = s_max[buf * kTcWarps];
+#pragma unroll
+            for (int w = 1; w < kTcWarps; ++w) m = fmaxf(m, s_max[buf * kTcWarps + w]);
+            int eb = (__float_as_int(m) >> 23) & 0xff;
+            eb = min(max(eb, 13), 254);
+            const float scale = __int_as_float((266 - eb) << 23);
+            if (tid == 0) s_inv[it_of_plane & 3] = __int_as_float((eb - 12) << 23);
+#pragma unroll
+            for (int j = 0; j < kF4PerThread; ++j) {
+                const int f = j * kTcThreads + tid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
+                const int h = f >> 5, w = (f & 31) << 2;
+                __half2 hi[2], lo[2];
+                split2(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
+                split2(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
+                const uint32_t off = tile_off(h, w);
+                *reinterpret_cast<uint2*>(smem + kOffO1 + off) = *reinterpret_cast<uint2*>(hi);
+                *reinterpret_cast<uint2*>(smem + kOffO2 + off) = *reinterpret_cast<uint2*>(lo);
+            }
+            fence_proxy_async();
+        };
+
+        fetch(0, first + stride);
+        convert(0, 0);
+        stamp();  // 2: first plane converted
+
+        int it = 0;
+        for (int p = first; p < a.planes; p += stride, ++it) {
+            const bool has_next = p + stride < a.planes;
+            tc_fence_before();
+            named_bar_sync(1, kTcThreads + 32);  // -> GEMM1(p)
+            stamp();                             // +0
+            mbar_wait(mbar_g1, it & 1);          // GEMM1(p) complete: D1 valid, X tiles free
+            if (it > 0) mbar_wait(mbar_g2 + ((it - 1) & 1), ((it - 1) >> 1) & 1);  // GEMM2(p - 1) complete: Z free
+            tc_fence_after();
+            stamp();                             // +2
+
+            // ---- split: D1 (fp32) -> Z^T hi | lo as packed fp16 back into TMEM (A operand of GEMM2: lane = w', K = h)
+            {
+                float z[32];
+                tmem_ld32_nowait(d1 + lane_base + col_base, z);
+                tmem_ld_wait(z);
+                uint32_t zh[16], zl[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    __half2 hi, lo;
+                    split2(z[2 * e], z[2 * e + 1], hi, lo);
+                    zh[e] = *reinterpret_cast<uint32_t*>(&hi);
+                    zl[e] = *reinterpret_cast<uint32_t*>(&lo);
+                }
+                tmem_st16(zp + lane_base + (col_base >> 1), zh);
+                tmem_st16(zp + 64 + lane_base + (col_base >> 1), zl);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            named_bar_sync(1, kTcThreads + 32);  // -> GEMM2(p)
+            stamp();                             // +3: split done
+            if (has_next) {
+                fetch((it + 1) & 1, p + 2 * stride);
+                stamp();                         // +4: next plane in registers
+                convert((it + 1) & 1, it + 1);
+            }
+            stamp();                             // +5: next plane converted
+        }
+        // ---- drain: all 16 compute warps store the last plane (one 32-column group each) ---------------------
+        {
+            const int last = it - 1, p_last = first + last * stride;
+            mbar_wait(mbar_g2 + (last & 1), (last >> 1) & 1);
+            tc_fence_after();
+            const float inv = s_inv[last & 3];
+            float* yp = a.y + static_cast<size_t>(p_last) * kP * kP + row;
             float o[32];
-            tmem_ld32_nowait(tmem + 256 + ((it - 1) & 1) * 128 + lane_base + col_base, o);
+            tmem_ld32_nowait(d2 + (last & 1) * 128 + lane_base + col_base, o);
             tmem_ld_wait(o);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o[j] * inv_prev);
+            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o[j] * inv);
         }
-        inv_prev = inv_scale;
-        stamp();  // +3: store(prev) done
-
-        mbar_wait(mbar_mma, par_mma);
-        par_mma ^= 1;
-        tc_fence_after();
-        stamp();  // +4: GEMM1 complete
-
-        // ---- split: D1 (fp32) -> Z^T hi | lo as packed fp16 back into TMEM (A operand of GEMM2: lane = w', K = h) ----
-        {
-            float z[32];
-            tmem_ld32_nowait(d1 + lane_base + col_base, z);
-            tmem_ld_wait(z);
-            uint32_t zh[16], zl[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                __half2 hi, lo;
-                split2(z[2 * e], z[2 * e + 1], hi, lo);
-                zh[e] = *reinterpret_cast<uint32_t*>(&hi);
-                zl[e] = *reinterpret_cast<uint32_t*>(&lo);
-            }
-            tmem_st16(tmem + 128 + lane_base + (col_base >> 1), zh);
-            tmem_st16(tmem + 128 + 64 + lane_base + (col_base >> 1), zl);
-            tmem_st_wait();
-        }
-        stamp();  // +5: split done (this thread)
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();  // -> the MMA warp issues GEMM2(p)
-        stamp();  // +6: barrier passed
-
-        // ---- fetch(p + stride) behind GEMM2(p), then start the TMA load of p + 2 stride ------------------------
-        if (p + stride < a.planes) {
-            fetch((it + 1) & 1);
-            if (tid == 0 && p + 2 * stride < a.planes) load_plane(p + 2 * stride);
-        }
-        stamp();  // +7: fetch(next) done
-
-        mbar_wait(mbar_mma, par_mma);
-        par_mma ^= 1;
-        tc_fence_after();
-        stamp();  // +8: GEMM2 complete
+        stamp();  // drain
     }
-    // ---- drain: the last plane's D2 --------------------------------------------------------------------------
-    {
-        const int p_last = first + (it - 1) * stride;
-        float* yp = a.y + static_cast<size_t>(p_last) * kP * kP + row;
-        float o[32];
-        tmem_ld32_nowait(tmem + 256 + ((it - 1) & 1) * 128 + lane_base + col_base, o);
-        tmem_ld_wait(o);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o[j] * inv_prev);
+    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) {
+        a.trace[0] = n_stamp;
+        a.trace[127] = static_cast<long long>(global_timer_ns());
+        a.trace[125] = clock64();
     }
-    stamp();  // drain done
-    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) a.trace[0] = n_stamp;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -477,8 +523,19 @@ int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff
     const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
     TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, y, planes, rule, std_eff, radius};
     const unsigned grid = static_cast<unsigned>(std::min(planes, device_sm_count()));
-    blur_tc128_kernel<<<grid, kCtaThreads, kSmemTc, stream>>>(a, tmap);
-    BGAN_LAUNCH_OK();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kCtaThreads);
+    cfg.dynamicSmemBytes = kSmemTc;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const char* no_pdl = getenv("BGAN_BLUR_NO_PDL");
+    cfg.attrs = attr;
+    cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel, a, tmap));
     return 0;
 }
 

@@ -20,13 +20,14 @@ cnt = t[0]
 st = t[1:1 + cnt]
 print("stamps", cnt)
 base = st[0]
-names = ["start", "prologue", "first-fetch"]
-per = ["convert", "barA", "store-prev", "G1done", "split", "barB", "fetch-next", "G2done"]
+names = ["start", "init+alloc", "taps", "chunk-table", "T-copied", "prologue", "first-convert"]
+per = ["barX", "G1done", "split+barZ", "fetch-next", "convert-next"]
 i = 0
 prev = base
-for k in range(3):
+print("clock: %.0f cycles in %.0f ns -> %.3f GHz" % (t[125] - st[0], t[127] - t[126], (t[125] - st[0]) / max(t[127] - t[126], 1)))
+for k in range(7):
     print("%-12s %8d  (+%d)" % (names[k], st[k] - base, st[k] - prev)); prev = st[k]
-i = 3
+i = 7
 it = 0
 NP = len(per)
 while cnt - i >= NP + 1:
