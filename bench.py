@@ -49,7 +49,7 @@ def parse_args():
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--no-swd", action="store_true", help="skip the secondary SWD timing")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--swd-images", type=int, default=4096, help="images per set for the secondary SWD timing")
+    p.add_argument("--swd-images", type=int, default=16384, help="images per set for the secondary SWD timing (BASELINE configs[4]: 16384)")
     p.add_argument("--stds", type=str, default="", help="comma-separated override of the std sweep (profiling runs)")
     return p.parse_args()
 

@@ -1,0 +1,124 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, `torch.distributed` (NCCL on GPUs, gloo in CPU tests).
+
+Blur: every image plane is independent, so a batch is simply sharded across ranks -- no collective on the data path
+(`shard_range`).  SWD has exactly one exchange step:
+
+  1. all-reduce (sum, fp64) of the per-channel sum / sum-of-squares of every level, so that every rank standardises
+     its descriptors with the statistics of the whole set (reference sliced_wasserstein.py:29-32);
+  2. all-gather of the standardised descriptors of every level;
+  3. every rank projects / sorts / diffs its own block of the dir_repeats x dirs_per_repeat directions, then the
+     per-repeat partial sums are all-reduced.
+
+The random stream stays bit-compatible with a single-process run: all ranks seed numpy identically and, at their
+k-th `feed`, draw the patch positions of all `world` minibatches of round k in rank order, keeping their own
+(`positions_for_round`).  The equivalent single-process run feeds the minibatches in the order
+rank0[k], rank1[k], ..., rank0[k+1], ...
+
+The helpers in this file are free of CUDA calls so that the host logic can be tested on CPU with gloo.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world_info(group=None) -> tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of n items for `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def positions_for_round(n_images: int, level_sizes, nhood_size: int, nhoods_per_image: int, rank: int, world: int):
+    """Patch centres of this rank's minibatch for every pyramid level: [(x, y), ...] in level order.
+
+    Draws, from numpy's global stream, exactly what a single process feeding the `world` minibatches of this round one
+    after the other would draw -- for each minibatch, for each level (finest first), x then y
+    (reference sliced_wasserstein.py:20-21,121-123) -- and keeps the draws of minibatch `rank`."""
+    half = nhood_size // 2
+    count = nhoods_per_image * n_images
+    mine = None
+    for r in range(world):
+        draws = []
+        for height, width in level_sizes:
+            x = np.random.randint(half, width - half, size=(count, 1, 1, 1))
+            y = np.random.randint(half, height - half, size=(count, 1, 1, 1))
+            draws.append((x.reshape(-1), y.reshape(-1)))
+        if r == rank:
+            mine = draws
+    return mine
+
+
+def direction_block(total_dirs: int, rank: int, world: int) -> slice:
+    """The block of projection directions (columns of the [dim, repeats * dirs_per_repeat] matrix) owned by `rank`."""
+    lo, hi = shard_range(total_dirs, rank, world)
+    return slice(lo, hi)
+
+
+def repeat_segments(block: slice, dirs_per_repeat: int):
+    """Split a direction block into (repeat index, local start, local stop) pieces that do not straddle repeats."""
+    out = []
+    d = block.start
+    while d < block.stop:
+        rep = d // dirs_per_repeat
+        stop = min(block.stop, (rep + 1) * dirs_per_repeat)
+        out.append((rep, d - block.start, stop - block.start))
+        d = stop
+    return out
+
+
+def _needs_host_staging(t: torch.Tensor, group=None) -> bool:
+    """gloo (CPU tests, single-GPU multi-process tests) moves CUDA tensors through the host; NCCL does not."""
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def all_reduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    if world_info(group)[1] > 1:
+        if _needs_host_staging(t, group):
+            h = t.cpu()
+            dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate the rows of every rank's [rows_r, k] tensor (rank-major).  Row counts may differ between ranks."""
+    rank, world = world_info(group)
+    if world == 1:
+        return t
+    if _needs_host_staging(t, group):
+        return all_gather_rows(t.cpu(), group).to(t.device)
+    t = t.contiguous()
+    counts = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    sizes = [int(c.item()) for c in all_counts]
+    if len(set(sizes)) == 1:
+        out = torch.empty((sizes[0] * world,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out
+    # unequal shards: pad to the largest, gather, drop the padding
+    biggest = max(sizes)
+    padded = torch.zeros((biggest,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    padded[: t.shape[0]] = t
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+def combine_repeat_sums(partial: torch.Tensor, rows: int, dirs_per_repeat: int, group=None) -> float:
+    """partial[r] = this rank's sum of |sorted A - sorted B| over its directions of repeat r (fp64).  Returns the
+    reference's `np.mean` over repeats of the per-repeat fp32 means (sliced_wasserstein.py:49-51)."""
+    all_reduce_sum_(partial, group)
+    per_repeat = (partial / float(rows * dirs_per_repeat)).to(torch.float32)
+    return float(np.float32(per_repeat.to(torch.float64).mean().item()))

@@ -173,8 +173,9 @@ def swd_extract(level: torch.Tensor, px, py, nhoods_per_image: int, nhood: int, 
     dev = level.device
     px_t = torch.as_tensor(np.ascontiguousarray(px, dtype=np.int32)).to(dev) if not torch.is_tensor(px) else px.to(dev, torch.int32)
     py_t = torch.as_tensor(np.ascontiguousarray(py, dtype=np.int32)).to(dev) if not torch.is_tensor(py) else py.to(dev, torch.int32)
+    px_t, py_t = px_t.contiguous(), py_t.contiguous()
     assert px_t.numel() == n * nhoods_per_image and py_t.numel() == n * nhoods_per_image
-    assert sums.dtype == torch.float64 and sums.numel() == 2 * c and sums.is_cuda
+    assert sums.dtype == torch.float64 and sums.numel() == 2 * c and sums.is_cuda and sums.is_contiguous()
     out = torch.empty((n * nhoods_per_image, c, nhood, nhood), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.load().bgan_swd_extract_f32(level.data_ptr(), n, c, h, w, px_t.data_ptr(), py_t.data_ptr(), nhoods_per_image,

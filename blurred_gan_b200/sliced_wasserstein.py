@@ -17,6 +17,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import dist as _dist
 from . import ops
 
 # ----------------------------------------------------------------------------
@@ -76,22 +77,27 @@ def _draw_directions(dim, dirs_per_repeat):
     return dirs.astype(np.float32)
 
 
-def sliced_wasserstein(A, B, dir_repeats, dirs_per_repeat):
-    """``sliced_wasserstein.py:38-51``: mean over repeats of mean |sort(A dirs) - sort(B dirs)|."""
+def sliced_wasserstein(A, B, dir_repeats, dirs_per_repeat, group=None):
+    """``sliced_wasserstein.py:38-51``: mean over repeats of mean |sort(A dirs) - sort(B dirs)|.
+
+    With a process group, A and B are the full (already all-gathered) descriptor sets on every rank and each rank
+    handles its own block of the ``dir_repeats * dirs_per_repeat`` directions; the per-repeat sums are all-reduced."""
     A = _to_device(A)
     B = _to_device(B, A.device)
     assert A.dim() == 2 and A.shape == B.shape  # (neighborhood, descriptor_component)
     rows, dim = A.shape
+    # every rank draws the same directions, in the reference's order: one randn(dim, dirs_per_repeat) per repeat
     dirs = np.concatenate([_draw_directions(dim, dirs_per_repeat) for _ in range(dir_repeats)], axis=1)
-    dirs_t = torch.from_numpy(dirs).to(A.device)
-    projA = ops.swd_sort_(ops.swd_project(A, dirs_t))  # [repeats * dirs, rows], each row sorted
-    projB = ops.swd_sort_(ops.swd_project(B, dirs_t))
-    sums = torch.cat([
-        ops.swd_absdiff_sum(projA[r * dirs_per_repeat : (r + 1) * dirs_per_repeat], projB[r * dirs_per_repeat : (r + 1) * dirs_per_repeat])
-        for r in range(dir_repeats)
-    ])
-    per_repeat = (sums / float(rows * dirs_per_repeat)).to(torch.float32)  # np.mean(dists) is fp32 in the reference
-    return np.float32(per_repeat.to(torch.float64).mean().item())
+    rank, world = _dist.world_info(group)
+    block = _dist.direction_block(dir_repeats * dirs_per_repeat, rank, world)
+    partial = torch.zeros(dir_repeats, dtype=torch.float64, device=A.device)
+    if block.stop > block.start:
+        dirs_t = torch.from_numpy(np.ascontiguousarray(dirs[:, block])).to(A.device)
+        projA = ops.swd_sort_(ops.swd_project(A, dirs_t))  # [directions of this rank, rows], each row sorted
+        projB = ops.swd_sort_(ops.swd_project(B, dirs_t))
+        for rep, lo, hi in _dist.repeat_segments(block, dirs_per_repeat):
+            partial[rep : rep + 1] += ops.swd_absdiff_sum(projA[lo:hi], projB[lo:hi])
+    return np.float32(_dist.combine_repeat_sums(partial, rows, dirs_per_repeat, group))
 
 
 # ----------------------------------------------------------------------------
@@ -146,12 +152,18 @@ def reconstruct_laplacian_pyramid(pyramid):
 
 
 class API:
-    """``sliced_wasserstein.py:98-133``: begin / feed / end state machine over a Laplacian pyramid."""
+    """``sliced_wasserstein.py:98-133``: begin / feed / end state machine over a Laplacian pyramid.
 
-    def __init__(self, image_shape, device=None):
+    ``group``: optional ``torch.distributed`` process group (or rely on the default group when it is initialised and
+    ``distributed=True``).  Every rank feeds its own shard of the images; see ``blurred_gan_b200/dist.py`` for the
+    exchange and for how the random stream stays identical to a single-process run."""
+
+    def __init__(self, image_shape, device=None, group=None, distributed=False):
         self.nhood_size, self.nhoods_per_image = 7, 128
         self.dir_repeats, self.dirs_per_repeat = 4, 128
         self.device = device
+        self.group = group
+        self.rank, self.world = _dist.world_info(group) if (distributed or group is not None) else (0, 1)
         # one pyramid level per power of two down to 16 px (image_shape = (C, H, W); H drives it, like the reference)
         self.resolutions = []
         size = image_shape[1]
@@ -168,19 +180,38 @@ class API:
     def begin(self, mode):
         assert mode in ['warmup', 'reals', 'fakes']
         self.descriptors = [[] for _ in self.resolutions]
-        self._sums = None  # per level: fp64 [sum_c..., sumsq_c...] accumulated on the device by the gather kernel
+        self._sums = None  # per level: fp64 [sum_c..., sumsq_c..., rows]; the statistics are accumulated on the device
+        self._rows = [0 for _ in self.resolutions]
 
     def feed(self, mode, minibatch):
         mb = _to_device(minibatch, self.device)
+        n, c = mb.shape[0], mb.shape[1]
+        assert mb.dim() == 4 and c == 3
         levels = generate_laplacian_pyramid(mb, len(self.resolutions))
         if self._sums is None:
-            self._sums = [torch.zeros(2 * mb.shape[1], dtype=torch.float64, device=mb.device) for _ in levels]
-        for lod, level in enumerate(levels):  # level order fixes the RNG order: x then y, finest level first
-            self.descriptors[lod].append(
-                get_descriptors_for_minibatch(level, self.nhood_size, self.nhoods_per_image, self._sums[lod]))
+            self._sums = [torch.zeros(2 * c + 1, dtype=torch.float64, device=mb.device) for _ in levels]
+        # All draws of this feed, in the reference's order (finest level first; x then y), packed into one upload.
+        pos = _dist.positions_for_round(n, [(lv.shape[2], lv.shape[3]) for lv in levels], self.nhood_size, self.nhoods_per_image,
+                                        self.rank, self.world)
+        count = n * self.nhoods_per_image
+        packed = torch.from_numpy(np.concatenate([np.concatenate(p) for p in pos]).astype(np.int32)).to(mb.device)
+        for lod, level in enumerate(levels):
+            px = packed[2 * lod * count : (2 * lod + 1) * count]
+            py = packed[(2 * lod + 1) * count : (2 * lod + 2) * count]
+            self.descriptors[lod].append(ops.swd_extract(level, px, py, self.nhoods_per_image, self.nhood_size, self._sums[lod][: 2 * c]))
+            self._rows[lod] += count
+
+    def _finalize(self, chunks, sums, rows_local):
+        """Standardise with the statistics of the whole (all-rank) set, then gather every rank's rows."""
+        desc = chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=0)
+        sums[-1] = float(rows_local)
+        _dist.all_reduce_sum_(sums, self.group)
+        rows_total = sums[-1:].cpu().item()  # exact in fp64
+        ops.swd_normalise_(desc, sums, rows_total * desc.shape[2] * desc.shape[3])
+        return _dist.all_gather_rows(desc.reshape(desc.shape[0], -1), self.group)
 
     def end(self, mode):
-        desc = [finalize_descriptors(d, s) for d, s in zip(self.descriptors, self._sums)]
+        desc = [self._finalize(d, s, r) for d, s, r in zip(self.descriptors, self._sums, self._rows)]
         del self.descriptors
         if mode in ['warmup', 'reals']:
             self.desc_real = desc
@@ -191,7 +222,7 @@ class API:
                     np.random.randn(d.shape[1], self.dirs_per_repeat)
             dist = [np.float32(0.0)] * len(desc)
         else:
-            dist = [sliced_wasserstein(real, fake, self.dir_repeats, self.dirs_per_repeat)
+            dist = [sliced_wasserstein(real, fake, self.dir_repeats, self.dirs_per_repeat, self.group)
                     for real, fake in zip(self.desc_real, desc)]
         scaled = [d * 1e3 for d in dist]
         return scaled + [np.mean(scaled)]

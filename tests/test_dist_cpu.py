@@ -1,0 +1,131 @@
+"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU path (blurred_gan_b200/dist.py).
+
+The compute here is the numpy oracle (allowed in tests only); what is under test is the exchange protocol: sharding,
+the replayed random stream, the all-reduce of channel statistics, the all-gather of rows, the direction blocks and
+the combination of per-repeat partial sums -- against a single-process oracle run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, uniform_pm1
+
+WORLD = 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from blurred_gan_b200 import dist as bd
+    from oracle import swd_oracle as so
+
+    assert bd.world_info() == (rank, world)
+    # ---- all_gather_rows with different row counts --------------------------------------------------------
+    t = torch.full((3 + rank, 2), float(rank))
+    g = bd.all_gather_rows(t)
+    assert g.shape == (3 + 4, 2) and torch.equal(g[:3], torch.zeros(3, 2)) and torch.equal(g[3:], torch.ones(4, 2))
+    # ---- distributed SWD protocol, oracle compute ------------------------------------------------------------
+    reals = uniform_pm1(41, (8, 3, 32, 32))
+    fakes = (0.7 * uniform_pm1(42, (8, 3, 32, 32)) + 0.05).astype(np.float32)
+    mb, levels, per_image, nhood, repeats, dpr = 2, 2, 16, 7, 4, 8
+    np.random.seed(123)
+
+    def collect(images):
+        # round k: rank r owns minibatch k * world + r
+        chunks = [[] for _ in range(levels)]
+        for k in range(len(images) // (mb * world)):
+            mine = images[(k * world + rank) * mb : (k * world + rank + 1) * mb]
+            pyr = so.generate_laplacian_pyramid(mine, levels)
+            pos = bd.positions_for_round(mb, [(lv.shape[2], lv.shape[3]) for lv in pyr], nhood, per_image, rank, world)
+            for lod, lv in enumerate(pyr):
+                chunks[lod].append(so.gather_descriptors(lv, pos[lod][0], pos[lod][1], nhood, per_image))
+        out = []
+        for lod in range(levels):
+            d = np.concatenate(chunks[lod]).astype(np.float64)
+            sums = torch.tensor(np.concatenate([d.sum((0, 2, 3)), (d ** 2).sum((0, 2, 3)), [d.shape[0]]]))
+            bd.all_reduce_sum_(sums)
+            cnt = sums[-1].item() * nhood * nhood
+            mean = (sums[:3] / cnt).numpy()
+            std = np.sqrt(sums[3:6].numpy() / cnt - mean ** 2)
+            dn = ((d - mean[None, :, None, None]) / std[None, :, None, None]).astype(np.float32)
+            out.append(bd.all_gather_rows(torch.from_numpy(dn.reshape(dn.shape[0], -1))).numpy())
+        return out
+
+    def distance(A, B):
+        dirs = np.concatenate([so.draw_directions(A.shape[1], dpr) for _ in range(repeats)], axis=1)
+        block = bd.direction_block(repeats * dpr, rank, world)
+        pa, pb = np.sort(A @ dirs[:, block], axis=0), np.sort(B @ dirs[:, block], axis=0)
+        partial = torch.zeros(repeats, dtype=torch.float64)
+        for rep, lo, hi in bd.repeat_segments(block, dpr):
+            partial[rep] += float(np.abs(pa[:, lo:hi] - pb[:, lo:hi]).astype(np.float64).sum())
+        return bd.combine_repeat_sums(partial, A.shape[0], dpr)
+
+    d_real = collect(reals)
+    for d in d_real:  # the reference's real-vs-real pass draws (and discards) its directions
+        for _ in range(repeats):
+            np.random.randn(d.shape[1], dpr)
+    d_fake = collect(fakes)
+    res = [distance(a, b) for a, b in zip(d_real, d_fake)]
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), np.array(res))
+    dist.destroy_process_group()
+
+
+def test_distributed_swd_protocol_matches_single_process(tmp_path):
+    from oracle import swd_oracle as so
+
+    mp.spawn(_worker, args=(WORLD, _free_port(), str(tmp_path)), nprocs=WORLD, join=True)
+    got = [np.load(tmp_path / ("rank%d.npy" % r)) for r in range(WORLD)]
+    np.testing.assert_array_equal(got[0], got[1])
+    # single-process oracle, minibatches fed in the same global order, same seed
+    reals = uniform_pm1(41, (8, 3, 32, 32))
+    fakes = (0.7 * uniform_pm1(42, (8, 3, 32, 32)) + 0.05).astype(np.float32)
+    rng = np.random.RandomState(123)
+
+    def collect(images):
+        chunks = [[] for _ in range(2)]
+        for i in range(0, len(images), 2):
+            for lod, lv in enumerate(so.generate_laplacian_pyramid(images[i : i + 2], 2)):
+                chunks[lod].append(so.get_descriptors_for_minibatch(lv, 7, 16, rng))
+        return [so.finalize_descriptors(c) for c in chunks]
+
+    d_real = collect(reals)
+    for d in d_real:
+        for _ in range(4):
+            rng.randn(d.shape[1], 8)
+    d_fake = collect(fakes)
+    want = [so.sliced_wasserstein(a, b, 4, 8, rng) for a, b in zip(d_real, d_fake)]
+    np.testing.assert_allclose(got[0], want, rtol=2e-5)  # (row order and fp64 statistics differ from numpy's fp32 means)
+
+
+def test_shard_and_direction_helpers():
+    from blurred_gan_b200 import dist as bd
+
+    for n in (0, 1, 7, 256, 768):
+        for world in (1, 2, 3, 8):
+            parts = [bd.shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+    covered = []
+    for r in range(3):
+        blk = bd.direction_block(512, r, 3)
+        for rep, lo, hi in bd.repeat_segments(blk, 128):
+            assert (blk.start + lo) // 128 == rep == (blk.start + hi - 1) // 128
+            covered += list(range(blk.start + lo, blk.start + hi))
+    assert covered == list(range(512))
+    assert bd.world_info() == (0, 1)

@@ -169,3 +169,55 @@ def test_api_matches_oracle_larger():
     got = _run_api(sw.API((3, 128, 128)), reals, fakes, 32)
     np.testing.assert_array_equal(got[0], want[0])
     np.testing.assert_allclose(got[1], want[1], rtol=1e-4)
+
+
+def _dist_worker(rank, world, port, out_dir):
+    import os
+    import sys
+
+    import torch.distributed as dist
+
+    from conftest import ROOT
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # two ranks share cuda:0; collectives staged through the host
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    reals = uniform_pm1(51, (16, 3, 64, 64))
+    fakes = (0.85 * uniform_pm1(52, (16, 3, 64, 64))).astype(np.float32)
+    mb = 4
+    np.random.seed(77)
+    api = sw.API((3, 64, 64), distributed=True)
+    assert (api.rank, api.world) == (rank, world)
+    api.begin("reals")
+    for k in range(len(reals) // (mb * world)):
+        api.feed("reals", reals[(k * world + rank) * mb : (k * world + rank + 1) * mb])
+    r0 = api.end("reals")
+    api.begin("fakes")
+    for k in range(len(fakes) // (mb * world)):
+        api.feed("fakes", torch.from_numpy(fakes[(k * world + rank) * mb : (k * world + rank + 1) * mb]).cuda())
+    r1 = api.end("fakes")
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), np.array([r0, r1], dtype=np.float64))
+    dist.destroy_process_group()
+
+
+def test_distributed_api_two_ranks_match_single_process(tmp_path):
+    """sharded feed, all-reduced statistics, all-gathered descriptors, direction blocks per rank."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_dist_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(tmp_path / ("rank%d.npy" % r)) for r in range(2)]
+    np.testing.assert_array_equal(got[0], got[1])
+    reals = uniform_pm1(51, (16, 3, 64, 64))
+    fakes = (0.85 * uniform_pm1(52, (16, 3, 64, 64))).astype(np.float32)
+    np.random.seed(77)
+    want = _run_api(so.API((3, 64, 64)), reals, fakes, 4)  # single process, same global minibatch order
+    np.testing.assert_array_equal(got[0][0], want[0])
+    np.testing.assert_allclose(got[0][1], want[1], rtol=1e-4)
