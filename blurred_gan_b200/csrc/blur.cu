@@ -31,7 +31,7 @@ namespace bgan {
 
 // blur_tc.cu: tcgen05 path for 128 x 128 planes
 bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, const float* x, const float* y);
-int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff, int radius, cudaStream_t stream);
+int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream);
 
 namespace {
 
@@ -559,7 +559,7 @@ extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int heigh
 
     if (blur_tc_eligible(g.planes, g.H, g.Wc, g.ES, radius, rule, x, y)) {
         g_last_path = 4;
-        return blur_tc_launch(x, y, g.planes, rule, std_eff, radius, stream);
+        return blur_tc_launch(x, y, g.planes, g.ES, rule, std_eff, radius, stream);
     }
     Plan fused = choose_plan(g.H, g.Wc, g.ES, radius, radius);
     if (fused.ok) {

@@ -63,7 +63,9 @@ constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) <<
 
 struct TcArgs {
     long long* trace;  // debug: clock64 stamps of CTA 0 / thread 0 (nullptr in production)
+    const float* x;    // only read directly for es > 1 (es == 1 goes through the tensor map)
     float* y;
+    int es;  // 1: planes are contiguous [128][128]; 3: NHWC, plane p = channel p % 3 of image p / 3 (interleaved floats)
     int planes;
     int rule;
     float std_eff;
@@ -197,6 +199,24 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t z_tmem, 
     for (int k = 1; k < 8; ++k) umma_f16_ts(d_tmem, a1 + 8 * k, db1 + k * kStep, 1);
 }
 
+// NHWC (es == 3): TMA cannot walk the innermost dimension with an element stride (elementStrides[0] is ignored for
+// non-interleaved maps) and the channel stride of 12 bytes is not a legal tensor-map stride either, so the compute
+// threads gather channel c of image n with 4-byte cp.async (LDGSTS) straight into the same row-major [128][128] staging
+// plane; completion is signalled on the same mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per thread).
+// The three channel planes of an image are consecutive work units, so neighbouring CTAs pull the same lines out of L2
+// at about the same time: DRAM still sees every byte once.
+__device__ __forceinline__ void gather_plane_load(unsigned char* stage, const float* x, uint64_t* bar, int plane, int es, int tid) {
+    const float* src = x + static_cast<size_t>(plane / es) * (kP * kP) * es + plane % es;
+    const uint32_t dst = smem_u32(stage) + tid * 4;
+#pragma unroll 8
+    for (int j = 0; j < kP * kP / kTcThreads; ++j) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + j * kTcThreads * 4),
+                     "l"(src + static_cast<size_t>(j * kTcThreads + tid) * es)
+                     : "memory");
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Warp-specialised software pipeline of one CTA over its planes p0, p1, ... :
 //
 //   compute warps 0-15          MMA warp 16                     store warps 17-20
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
-        mbar_init(mbar_tma, 1);
+        mbar_init(mbar_tma, a.es == 1 ? 1 : kTcThreads);  // TMA transaction bytes / one cp.async arrival per compute thread
         mbar_init(mbar_g1, 1);
         mbar_init(mbar_g2 + 0, 1);
         mbar_init(mbar_g2 + 1, 1);
@@ -244,9 +264,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         mbar_init(mbar_d2free + 1, kStoreWarps);
         mbar_fence_init();
         // the first plane starts moving before anything else is set up (but not before the producer of x is done)
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-        tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, blockIdx.x);
+        if (a.es == 1) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+            tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, static_cast<int>(blockIdx.x));
+        }
     }
     __syncwarp();
     if (warp == 0) {  // TMEM columns: D1 = [0, 128), Z^T as fp16 hi | lo = [128, 256), D2 double-buffered = [256, 384) / [384, 512)
@@ -269,6 +291,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         for (int t = lane; t < n_taps; t += 32) s_g[t] = s_g[t] / tot;
     }
     __syncthreads();
+    if (a.es != 1 && warp < kTcWarps) {  // (mbarrier init is visible now)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        gather_plane_load(smem + kOffStage, a.x, mbar_tma, static_cast<int>(blockIdx.x), a.es, tid);
+    }
     stamp();  // taps ready
     // ---- chunk table: a 16-byte chunk of T (row, K = 8c .. 8c+7) holds taps d0 .. d0+7 with d0 = 8c - row + r, so there
     // are only n_taps + 7 distinct non-zero chunks.  Build them once (fp16 hi | lo), then T1 / T2 are plain copies. ----
@@ -332,7 +358,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             mbar_wait(mbar_g2 + (it & 1), (it >> 1) & 1);
             tc_fence_after();
             const float inv = s_inv[it & 3];
-            float* yp = a.y + static_cast<size_t>(p) * kP * kP + row;
+            float* yp = a.y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
+            const size_t ld = static_cast<size_t>(kP) * a.es;  // floats between consecutive output rows h'
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 float o[32];
@@ -344,7 +371,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
                     if (lane == 0) mbar_arrive(mbar_d2free + (it & 1));
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(c * 32 + j) * kP, o[j] * inv);
+                for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(c * 32 + j) * ld, o[j] * inv);
             }
         }
     } else {
@@ -368,7 +395,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) s_max[buf * kTcWarps + warp] = m;
             named_bar_sync(2, kTcThreads);
-            if (tid == 0 && next_plane < a.planes) {
+            if (a.es != 1) {
+                if (next_plane < a.planes) gather_plane_load(smem + kOffStage, a.x, mbar_tma, next_plane, a.es, tid);
+            } else if (tid == 0 && next_plane < a.planes) {
                 mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
                 tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, next_plane);
                 if (next_plane + stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, next_plane + stride);  // warm L2 one more ahead
@@ -445,12 +474,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             mbar_wait(mbar_g2 + (last & 1), (last >> 1) & 1);
             tc_fence_after();
             const float inv = s_inv[last & 3];
-            float* yp = a.y + static_cast<size_t>(p_last) * kP * kP + row;
+            float* yp = a.y + (static_cast<size_t>(p_last / a.es) * kP * kP + row) * a.es + p_last % a.es;
+            const size_t ld = static_cast<size_t>(kP) * a.es;
             float o[32];
             tmem_ld32_nowait(d2 + (last & 1) * 128 + lane_base + col_base, o);
             tmem_ld_wait(o);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * kP, o[j] * inv);
+            for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(col_base + j) * ld, o[j] * inv);
         }
         stamp();  // drain
     }
@@ -496,16 +526,19 @@ bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, c
     if (off && atoi(off)) return false;
     const char* min_r = getenv("BGAN_BLUR_TC_MIN_R");
     const int rmin = min_r ? atoi(min_r) : 0;
-    return ES == 1 && H == kP && Wc == kP && planes > 0 && radius >= rmin && radius <= 127 &&
+    return (ES == 1 || ES == 3) && H == kP && Wc == kP * ES && planes > 0 && radius >= rmin && radius <= 127 &&
            (rule == BGAN_RULE_TORCH || rule == BGAN_RULE_TF) && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
            reinterpret_cast<uintptr_t>(y) % 16 == 0 && encode_fn() != nullptr;
 }
 
-int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff, int radius, cudaStream_t stream) {
+// `planes` counts geometry planes: N*C for NCHW (es = 1), N images of 128 x 384 interleaved floats for NHWC (es = 3)
+int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     bind_primary_context();
-    const cuuint64_t dims[3] = {kP, kP, static_cast<cuuint64_t>(planes)};
+    // the tensor map is only used for es == 1; for NHWC it describes the same memory as dense 128-float rows (never loaded)
+    const cuuint64_t rows = static_cast<cuuint64_t>(planes) * es;
+    const cuuint64_t dims[3] = {kP, kP, rows};
     const cuuint64_t strides[2] = {kP * 4, kP * kP * 4};
     const cuuint32_t box[3] = {kP, kP, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
@@ -521,8 +554,17 @@ int blur_tc_launch(const float* x, float* y, int planes, int rule, float std_eff
         attr_dev = dev;
     }
     const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
-    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, y, planes, rule, std_eff, radius};
-    const unsigned grid = static_cast<unsigned>(std::min(planes, device_sm_count()));
+    const int units = planes * es;  // 128 x 128 channel planes
+    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, x, y, es, units, rule, std_eff, radius};
+    // balanced persistent grid: every CTA runs the same number of rounds (768 planes on 148 SMs -> 128 CTAs x 6 planes
+    // rather than 28 CTAs x 6 + 120 x 5), so that the HBM-bound steady state has no latency-bound tail round
+    const int sms = device_sm_count();
+    const int rounds = ceil_div(units, sms);
+    int grid_i = ceil_div(units, rounds);
+    if (const char* g = getenv("BGAN_TC_GRID")) {
+        if (atoi(g) > 0) grid_i = std::min(std::min(atoi(g), units), sms);
+    }
+    const unsigned grid = static_cast<unsigned>(grid_i);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);

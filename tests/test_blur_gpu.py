@@ -273,3 +273,25 @@ def test_tensor_core_path_matches_oracle_and_fma_path(std):
     got_tf = blur_images(_dev(xt), std)
     assert ops.last_blur_path() == 4
     assert_close(got_tf, bo.blur_images_tf_ref(xt, std), "tensor-core path, tf rule, std=%g" % std)
+
+
+@pytest.mark.parametrize("std", [0.5, 3.0, 23.0])
+def test_tensor_core_path_nhwc(std):
+    """NHWC 128 x 128 x 3 (the layout of the reference's Keras layer): TMA deinterleaves with element stride 3."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D
+
+    x = uniform_pm1(30, (5, 128, 128, 3))
+    x[1] *= 1e-5
+    layer = GaussianBlur2D(std).cuda()
+    xd = _dev(x).requires_grad_(True)
+    y = layer(xd)
+    assert ops.last_blur_path() == 4
+    want = bo.blur_images_tf_ref(x, std)
+    for n in range(x.shape[0]):
+        assert_close(y[n], want[n], "NHWC tensor-core path image %d std=%g" % (n, std))
+    g = uniform_pm1(31, x.shape)
+    y.backward(_dev(g))
+    assert_close(xd.grad, bo.blur_images_tf_ref(g, std), "NHWC tensor-core backward std=%g" % std)
+    x1 = uniform_pm1(32, (4, 128, 128, 1))
+    assert_close(layer(_dev(x1)), bo.blur_images_tf_ref(x1, std), "NHWC C=1 std=%g" % std)
