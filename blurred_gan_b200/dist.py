@@ -122,3 +122,21 @@ def combine_repeat_sums(partial: torch.Tensor, rows: int, dirs_per_repeat: int, 
     all_reduce_sum_(partial, group)
     per_repeat = (partial / float(rows * dirs_per_repeat)).to(torch.float32)
     return float(np.float32(per_repeat.to(torch.float64).mean().item()))
+
+
+def allreduce_gradients(params, group=None) -> None:
+    """Data-parallel gradient exchange of the train-step harness (BASELINE configs[2]): one flat all-reduce (sum) of
+    the gradients of `params`.  The reference divides its losses by the *global* batch size (wgan.py:130,157), so the
+    sum over ranks is the gradient of the global batch -- no averaging."""
+    if world_info(group)[1] == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    all_reduce_sum_(flat, group)
+    offset = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[offset:offset + n].view_as(g))
+        offset += n

@@ -1,0 +1,186 @@
+"""Train-step harness (N1 WGAN-GP step, N2 sigma controllers, N4 SWD metric).
+
+CPU tests run the harness with the *oracle's* blur layer (the reference's two F.conv2d calls) because the package has no
+CPU path; the GPU test runs the same step through the B200 blur and checks it against the oracle-blur step with
+identical weights, latents and dropout masks.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from blurred_gan_b200 import callbacks, nets
+from blurred_gan_b200.blurred_gan import BlurredWGAN, BlurredWGANGP
+from blurred_gan_b200.wgan import WGANGP, gradient_penalty
+from oracle import blur_oracle as bo
+
+
+class OracleBlur2D(nn.Module):
+    """CPU stand-in for GaussianBlur2D: TF-rule plan (gaussian_blur.py:50-80) + explicit-tap depthwise F.conv2d."""
+
+    def __init__(self, initial_std=0.01):
+        super().__init__()
+        self.std = nn.Parameter(torch.tensor(float(initial_std)), requires_grad=False)
+        self.calls = 0
+
+    def assign(self, value):
+        self.std.data.fill_(float(value))
+
+    def forward(self, x):
+        self.calls += 1
+        n, c, h, w = x.shape
+        taps = torch.from_numpy(bo.taps_for(bo.RULE_TF, float(self.std.item()), h, w)).to(x)
+        r = taps.numel() // 2
+        kv = taps.view(1, 1, -1, 1).repeat(c, 1, 1, 1)
+        kh = taps.view(1, 1, 1, -1).repeat(c, 1, 1, 1)
+        y = torch.nn.functional.conv2d(x, kv, padding=(r, 0), groups=c)  # vertical first (gaussian_blur.py:116-130)
+        return torch.nn.functional.conv2d(y, kh, padding=(0, r), groups=c)
+
+
+class CountingBlur(OracleBlur2D):
+    """Counts blur applications including backward and double backward (the operator is self-adjoint)."""
+
+    def forward(self, x):
+        outer = self
+        taps = torch.from_numpy(bo.taps_for(bo.RULE_TF, float(self.std.item()), x.shape[2], x.shape[3])).to(x)
+
+        class Op(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, t):
+                outer.applications += 1
+                return OracleBlur2D.forward(outer, t)
+
+            @staticmethod
+            def backward(ctx, g):
+                return Op.apply(g)
+
+        return Op.apply(x)
+
+
+def _mnist_gan(blur, batch=64, cls=BlurredWGANGP):
+    torch.manual_seed(0)
+    hp = cls.HyperParameters(batch_size=batch, global_batch_size=batch, initial_blur_std=23.0)
+    return cls(nets.MnistGenerator(), nets.MnistDiscriminator(), hp, blur=blur)
+
+
+def test_nets_have_the_reference_shapes():
+    g, d = nets.MnistGenerator(), nets.MnistDiscriminator()
+    z = torch.rand(4, 100)
+    g.eval()
+    assert g(z).shape == (4, 1, 28, 28) and d(g(z)).shape == (4, 1)
+    gc, dc = nets.CelebaGenerator(), nets.CelebaDiscriminator()
+    gc.eval()
+    x = gc(torch.rand(2, 100))
+    assert x.shape == (2, 3, 128, 128) and dc(x).shape == (2, 1)
+    # parameter counts quoted in SURVEY section 2 (demo_celeba.py nets: ~11.7 M / ~4.4 M)
+    assert abs(sum(p.numel() for p in gc.parameters()) / 1e6 - 11.7) < 0.3
+    assert abs(sum(p.numel() for p in dc.parameters()) / 1e6 - 4.4) < 0.2
+
+
+def test_cfg1_mnist_step_on_cpu_issues_seven_blurs_and_anneals():
+    """BASELINE configs[0]: demo_mnist-shaped blurred WGAN-GP step, batch 64 x 28 x 28 x 1, std annealed 23 -> 0, on CPU."""
+    blur = CountingBlur(23.0)
+    blur.applications = 0
+    gan = _mnist_gan(blur)
+    sched = callbacks.LinearBlurSchedule(total_batches=3, max_value=23.0, min_value=0.0)
+    sched.set_model(gan)
+    rng = np.random.RandomState(0)
+    stds = []
+    for step in range(3):
+        sched.on_batch_begin()
+        stds.append(float(gan.std.item()))
+        before = blur.applications
+        reals = torch.from_numpy((rng.rand(64, 1, 28, 28) * 2 - 1).astype(np.float32))
+        gan.train_on_batch(reals)
+        assert blur.applications - before == 7  # 3 fwd + 1 bwd + 1 double-bwd (critic), 1 fwd + 1 bwd (generator)
+        m = gan.metric_results()
+        assert all(math.isfinite(v) for v in m.values()), m
+        assert m["std"] == pytest.approx(stds[-1])
+    assert stds == pytest.approx([23.0, 11.5, 0.0])
+    assert gan.n_img == 192 and gan.n_batches == 3
+
+
+def test_drift_term_is_a_vector_like_the_reference():
+    gan = _mnist_gan(OracleBlur2D(1.0), batch=8)
+    reals = torch.rand(8, 1, 28, 28) * 2 - 1
+    gan.batch_size = 8
+    fakes = gan.generate_samples(training=False).detach()
+    loss = gan.discriminator_loss(reals, fakes, gan._scores(reals, True), gan._scores(fakes, True))
+    assert loss.shape == (8,)  # wgan.py:282-284: scalar + [B] vector
+    plain = BlurredWGAN(nets.MnistGenerator(), nets.MnistDiscriminator(), BlurredWGAN.HyperParameters(global_batch_size=8), blur=OracleBlur2D(1.0))
+    plain.batch_size = 8
+    assert plain.discriminator_loss(reals, fakes, torch.ones(8, 1), torch.zeros(8, 1)).item() == pytest.approx(-1.0)
+
+
+def test_gradient_penalty_of_a_linear_critic():
+    w = torch.randn(1, 1, 28, 28)
+    critic = lambda x: (x * w).sum(dim=(1, 2, 3)).unsqueeze(1)  # noqa: E731
+    critic.train = lambda mode=True: None
+    gp = gradient_penalty(critic, torch.rand(5, 1, 28, 28), torch.rand(5, 1, 28, 28))
+    assert gp.item() == pytest.approx((w.norm().item() - 1.0) ** 2, rel=1e-5)
+
+
+def test_blur_decay_controller_matches_the_keras_schedule():
+    ctl = callbacks.BlurDecayController(total_n_training_examples=60000 * 10, max_value=5.0)
+    # tf.keras ExponentialDecay(5, decay_steps=60000, 0.96)(step) = 5 * 0.96 ** (step / 60000)
+    assert ctl.schedule(0) == 5.0
+    assert ctl.schedule(18750) == pytest.approx(5.0 * 0.96 ** (18750 / 60000.0))  # 10 epochs of batch 32: sigma only falls to 0.987 * max
+    assert ctl.schedule(18750) / 5.0 == pytest.approx(0.9873, abs=1e-3)
+
+
+def test_adaptive_controller_tracks_but_does_not_assign_by_default():
+    gan = _mnist_gan(OracleBlur2D(23.5), batch=4)
+    ctl = callbacks.AdaptiveBlurController(warmup_n_batches=0)
+    ctl.set_model(gan)
+    ctl.on_train_begin()
+    assert float(gan.std.item()) == 23.5
+    for b in range(250):
+        ctl.on_batch_end(b, {"fake_scores": 1.0, "real_scores": 1.0})  # ratio 0.5: "stable"
+    # lowered once at batch 100 and once at batch 200 (delay_between_modifications = 100)
+    assert ctl.std == pytest.approx(23.5 * 0.99 ** 2)
+    assert float(gan.std.item()) == 23.5  # callbacks.py:102-103: the assignment is disabled in the reference
+
+
+@pytest.mark.gpu
+def test_celeba_step_on_gpu_matches_the_oracle_blur_step():
+    """BASELINE configs[2] shape (small batch): the step through the B200 blur == the step through the oracle blur."""
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D
+
+    results = []
+    for kind in ("b200", "oracle"):
+        torch.manual_seed(0)
+        blur = GaussianBlur2D(3.0) if kind == "b200" else OracleBlur2D(3.0)
+        hp = BlurredWGANGP.HyperParameters(batch_size=8, global_batch_size=8, initial_blur_std=3.0)
+        gan = BlurredWGANGP(nets.CelebaGenerator(), nets.CelebaDiscriminator(), hp, blur=blur).cuda()
+        torch.manual_seed(1)
+        reals = torch.rand(8, 3, 128, 128, device="cuda") * 2 - 1
+        torch.manual_seed(2)
+        gan.train_on_batch(reals)
+        results.append((gan.metric_results(), [p.detach().clone() for p in gan.discriminator[1].parameters()]))
+    (m0, p0), (m1, p1) = results
+    for k in m0:
+        assert m0[k] == pytest.approx(m1[k], rel=2e-3, abs=1e-5), k
+    for a, b in zip(p0, p1):
+        # one Adam step moves every weight by ~lr; what is compared is the direction, which depends on the blurred gradients
+        assert (a - b).abs().max().item() <= 2e-3 * 1.01
+        assert ((a - b).abs() > 1e-4).float().mean().item() < 0.02
+
+
+@pytest.mark.gpu
+def test_swd_metric_on_device_tensors():
+    from blurred_gan_b200.metrics import SWDMetric
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    m = SWDMetric((3, 64, 64))
+    for _ in range(2):
+        m.update_state(torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1, torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1)
+    res = m.result()
+    assert len(res) == len(m.metric_names()) and all(math.isfinite(v) and v > 0 for v in res)
+    same = SWDMetric((3, 64, 64))
+    x = torch.rand(16, 3, 64, 64, device="cuda")
+    same.update_state(x, x)
+    np.random.seed(0)
+    assert same.result()[-1] < res[-1]
