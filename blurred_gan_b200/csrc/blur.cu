@@ -33,6 +33,11 @@ namespace bgan {
 bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, const float* x, const float* y);
 int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream);
 
+// blur_direct.cu: FFMA path for 128 x 128 images and radius <= 4
+bool blur_direct_eligible(int planes, int H, int Wc, int ES, int radius, const float* x, const float* y);
+int blur_direct_launch(const float* x, float* y, int planes, int es, int radius, int rule, float std_eff, const float* taps_dev,
+                       cudaStream_t stream);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -557,6 +562,10 @@ extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int heigh
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     bool tma = false;
 
+    if (blur_direct_eligible(g.planes, g.H, g.Wc, g.ES, radius, x, y)) {
+        g_last_path = 5;
+        return blur_direct_launch(x, y, g.planes, g.ES, radius, rule, std_eff, taps_device, stream);
+    }
     if (blur_tc_eligible(g.planes, g.H, g.Wc, g.ES, radius, rule, x, y)) {
         g_last_path = 4;
         return blur_tc_launch(x, y, g.planes, g.ES, rule, std_eff, radius, stream);

@@ -1,0 +1,296 @@
+// Direct (CUDA-core) separable blur for 128 x 128 images and small radii (r <= 5 NCHW, r <= 4 NHWC).
+//
+// The tensor-core kernel (blur_tc.cu) costs the same ~26 us per 768-plane launch for every tap count; for the few-tap
+// blurs at the end of the sigma annealing (the reference's real operating range is sigma <= 5, SURVEY Q12, and its
+// default initial sigma of 0.05 gives 3 taps) a plain FFMA kernel is cheaper than two 128^3 GEMMs: 2 (2r + 1) FMAs
+// per pixel is far below the HBM time for r <= 4, so this kernel is a copy with a little arithmetic on the way.
+//
+// Per CTA (persistent, one per SM): a producer warp streams units -- a whole NCHW plane, or half an NHWC image --
+// into a ring of shared-memory buffers with TMA.  The box starts r rows above the unit and ends r rows below it, and
+// TMA zero-fills what lies outside the image, which is exactly the reference's zero "same" padding in the vertical
+// direction.  Eight consumer warps (NCHW: two groups of four, each group on its own plane) each own a band of rows; a
+// lane owns four pixels (4 * ES consecutive floats) of every row of the band.  For each input row the lane loads its
+// window -- NCHW: aligned LDS.128 from rows staged with zero columns either side (TMA again); NHWC: its own floats plus
+// the 3 r floats either side from its neighbour lanes by shuffle, zero at the image border -- forms the horizontally
+// blurred row in registers, and as soon as 2r + 1 of those exist, the vertically blurred output row, stored with
+// 16-byte coalesced streaming stores.  The row loop is fully unrolled, so the sliding window of 2r + 1 blurred rows lives in
+// registers under static names; the intermediate never touches shared memory.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "taps.cuh"
+
+namespace bgan {
+namespace {
+
+constexpr int kD = 128;            // image edge
+constexpr int kConsumerWarps = 8;
+constexpr int kDirectThreads = (kConsumerWarps + 1) * 32;
+
+// ES == 1 (NCHW planes, NHWC with one channel): the staged rows carry `pad` zero floats on either side (TMA fills what
+// lies outside the image), so a lane reads its whole window with aligned LDS.128 and no border logic.
+// ES == 3 (NHWC): a lane owns 12 floats and gets the 3 r floats either side from its neighbour lanes by shuffle.
+template <int ES>
+struct DirectCfg {
+    static constexpr int kRowFloats = kD * ES;                 // floats per image row
+    static constexpr int kGroups = ES == 1 ? 2 : 1;            // consumer warp groups, each working on its own unit
+    static constexpr int kGroupWarps = kConsumerWarps / kGroups;
+    static constexpr int kRowsPerWarp = ES == 1 ? 32 : 8;      // output rows owned by one consumer warp (the r rows above
+                                                               // and below are blurred horizontally a second time by the
+                                                               // neighbour warp: taller bands, less redundancy)
+    static constexpr int kUnitRows = kGroupWarps * kRowsPerWarp;  // 128 (whole plane) / 64 (half an NHWC image)
+    static constexpr int kUnitsPerImage = kD / kUnitRows;      // 1 / 2
+    static constexpr int kPanels = ES == 1 ? 1 : 2;            // TMA boxes span at most 256 elements: NHWC rows are two boxes
+    static constexpr int kPanelFloats = kRowFloats / kPanels;  // 128 / 192
+    static constexpr int kLanesPerPanel = 32 / kPanels;
+    __host__ __device__ static constexpr int pad(int r) { return ES == 1 ? (r <= 4 ? 4 : 8) : 0; }
+    __host__ __device__ static constexpr int pitch(int r) { return kPanelFloats + 2 * pad(r); }  // floats per staged (panel) row
+    __host__ __device__ static constexpr int stages(int r) { return ES == 1 && r <= 4 ? 3 : 2; }
+    __host__ __device__ static constexpr int box_rows(int r) { return kUnitRows + 2 * r; }
+    __host__ __device__ static constexpr size_t panel_bytes(int r) { return (static_cast<size_t>(box_rows(r)) * pitch(r) * sizeof(float) + 127) / 128 * 128; }
+    __host__ __device__ static constexpr size_t stage_bytes(int r) { return panel_bytes(r) * kPanels; }  // (TMA destinations: 128-byte aligned)
+    __host__ __device__ static constexpr size_t smem_bytes(int r) { return stages(r) * stage_bytes(r) + 1024; }
+};
+
+struct DirectArgs {
+    float* y;
+    const float* taps_dev;
+    int units;  // planes (NCHW) or 2 * images (NHWC)
+    int rule;
+    float std_eff;
+};
+
+template <int ES, int R>
+__global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const DirectArgs a, const __grid_constant__ CUtensorMap tmap) {
+    using C = DirectCfg<ES>;
+    constexpr int kTaps = 2 * R + 1;
+    constexpr int kLaneFloats = 4 * ES;      // floats of one row owned by a lane (4 pixels)
+    constexpr int kHalo = ES * R;            // floats needed from the neighbour lane on either side
+    constexpr int kRows = C::kRowsPerWarp + 2 * R;  // input rows a warp walks through
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int kStages = C::stages(R), kPad = C::pad(R), kPitch = C::pitch(R);
+    unsigned char* misc = smem + kStages * C::stage_bytes(R);
+    float* s_g = reinterpret_cast<float*>(misc);                  // taps (<= 9)
+    double* s_red = reinterpret_cast<double*>(misc + 64);
+    uint64_t* full = reinterpret_cast<uint64_t*>(misc + 128);     // [kStages]
+    uint64_t* empty = full + kStages;                             // [kStages]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n_it = (a.units - first + stride - 1) / stride;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int b = 0; b < kStages; ++b) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, C::kGroupWarps);
+        }
+        mbar_fence_init();
+    }
+    if (a.rule == BGAN_RULE_EXPLICIT) asm volatile("griddepcontrol.wait;" ::: "memory");  // (the taps are read from global memory)
+    normalised_taps(a.rule, a.std_eff, R, a.taps_dev, s_g, s_red);  // ends with __syncthreads(): barrier init is visible too
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // x may be written, y may still be read by the previous grid
+
+    if (warp == kConsumerWarps) {
+        // ================= producer: one elected lane feeds the ring =================================
+        if (lane == 0) {
+            for (int it = 0; it < n_it; ++it) {
+                const int b = it % kStages, use = it / kStages;
+                if (use > 0) mbar_wait(empty + b, (use - 1) & 1);
+                const int unit = first + it * stride;
+                const int image = unit / C::kUnitsPerImage, row0 = (unit % C::kUnitsPerImage) * C::kUnitRows - R;
+                unsigned char* dst = smem + b * C::stage_bytes(R);
+                mbar_arrive_expect_tx(full + b, static_cast<uint32_t>(C::box_rows(R) * kPitch * C::kPanels * sizeof(float)));
+#pragma unroll
+                for (int p = 0; p < C::kPanels; ++p)
+                    tma_load_3d(dst + p * C::panel_bytes(R), &tmap, full + b, p * C::kPanelFloats - kPad, row0, image);
+            }
+        }
+        return;
+    }
+
+    // ================= consumers ========================================================================
+    float g[kTaps];
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) g[t] = s_g[t];
+    // this lane's floats inside a staged row: panel (NHWC rows are split into two boxes) and offset within it
+    const int panel = lane / C::kLanesPerPanel;
+    const int lane_off = panel * static_cast<int>(C::panel_bytes(R) / sizeof(float)) + (lane % C::kLanesPerPanel) * kLaneFloats;  // (window start for ES == 1)
+
+    const int group = warp / C::kGroupWarps, gwarp = warp % C::kGroupWarps;
+    for (int it = group; it < n_it; it += C::kGroups) {
+        const int b = it % kStages, use = it / kStages;
+        const int unit = first + it * stride;
+        const int image = unit / C::kUnitsPerImage, out_row0 = (unit % C::kUnitsPerImage) * C::kUnitRows + gwarp * C::kRowsPerWarp;
+        mbar_wait(full + b, use & 1);
+        const float* src = reinterpret_cast<const float*>(smem + b * C::stage_bytes(R)) + lane_off + gwarp * C::kRowsPerWarp * kPitch;
+        float* dst = a.y + (static_cast<size_t>(image) * kD + out_row0) * C::kRowFloats + lane * kLaneFloats;
+
+        float hrow[kRows][kLaneFloats];  // horizontally blurred rows; only 2r + 1 of them are live at any time
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+            // win[kOff + o + ES * (t - r)] is the input of output float o under tap t
+            constexpr int kWin = ES == 1 ? 4 + 2 * kPad : kLaneFloats + 2 * kHalo;
+            constexpr int kOff = ES == 1 ? kPad : kHalo;
+            float win[kWin];
+            if constexpr (ES == 1) {
+#pragma unroll
+                for (int q = 0; q < kWin / 4; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + i * kPitch + 4 * q);
+                    win[4 * q + 0] = v.x;
+                    win[4 * q + 1] = v.y;
+                    win[4 * q + 2] = v.z;
+                    win[4 * q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < ES; ++q) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + i * kPitch + 4 * q);
+                    win[kHalo + 4 * q + 0] = v.x;
+                    win[kHalo + 4 * q + 1] = v.y;
+                    win[kHalo + 4 * q + 2] = v.z;
+                    win[kHalo + 4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int k = 0; k < kHalo; ++k) {
+                    const float l = __shfl_up_sync(0xffffffffu, win[kLaneFloats + k], 1);    // neighbour's last kHalo floats
+                    const float r = __shfl_down_sync(0xffffffffu, win[kHalo + k], 1);        // neighbour's first kHalo floats
+                    win[k] = lane == 0 ? 0.0f : l;
+                    win[kHalo + kLaneFloats + k] = lane == 31 ? 0.0f : r;
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kLaneFloats; ++o) {
+                float acc = g[0] * win[kOff - kHalo + o];
+#pragma unroll
+                for (int t = 1; t < kTaps; ++t) acc = fmaf(g[t], win[kOff - kHalo + o + ES * t], acc);
+                hrow[i][o] = acc;
+            }
+            if (i >= 2 * R) {
+                const int j = i - 2 * R;  // output row of the band: taps over hrow[j .. j + 2r]
+                float out[kLaneFloats];
+#pragma unroll
+                for (int o = 0; o < kLaneFloats; ++o) {
+                    float acc = g[0] * hrow[j][o];
+#pragma unroll
+                    for (int t = 1; t < kTaps; ++t) acc = fmaf(g[t], hrow[j + t][o], acc);
+                    out[o] = acc;
+                }
+#pragma unroll
+                for (int q = 0; q < ES; ++q)
+                    __stcs(reinterpret_cast<float4*>(dst + static_cast<size_t>(j) * C::kRowFloats) + q,
+                           make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + b);
+    }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn direct_encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <int ES, int R>
+int launch_direct(const float* x, float* y, int images, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
+    using C = DirectCfg<ES>;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    thread_local bool bound = false;  // cuTensorMapEncodeTiled needs a context bound to the calling thread
+    if (!bound) {
+        cudaFree(nullptr);
+        bound = true;
+    }
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(C::kRowFloats), kD, static_cast<cuuint64_t>(images)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(C::kRowFloats) * 4, static_cast<cuuint64_t>(C::kRowFloats) * kD * 4};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(C::pitch(R)), static_cast<cuuint32_t>(C::box_rows(R)), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult res = direct_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);  // out-of-bounds rows read as zeros
+    BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
+    auto kernel = blur_direct128_kernel<ES, R>;
+    thread_local int attr_dev = -1;
+    int dev = 0;
+    BGAN_CUDA_OK(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        BGAN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem_bytes(R))));
+        attr_dev = dev;
+    }
+    const int units = images * C::kUnitsPerImage;
+    DirectArgs a{y, taps_dev, units, rule, std_eff};
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(std::min(units, device_sm_count())));
+    cfg.blockDim = dim3(kDirectThreads);
+    cfg.dynamicSmemBytes = C::smem_bytes(R);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const char* no_pdl = getenv("BGAN_BLUR_NO_PDL");
+    cfg.attrs = attr;
+    cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, tmap));
+    return 0;
+}
+
+template <int ES>
+int launch_direct_r(const float* x, float* y, int images, int radius, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
+    switch (radius) {
+        case 1: return launch_direct<ES, 1>(x, y, images, rule, std_eff, taps_dev, stream);
+        case 2: return launch_direct<ES, 2>(x, y, images, rule, std_eff, taps_dev, stream);
+        case 3: return launch_direct<ES, 3>(x, y, images, rule, std_eff, taps_dev, stream);
+        case 4: return launch_direct<ES, 4>(x, y, images, rule, std_eff, taps_dev, stream);
+        default: break;
+    }
+    if constexpr (ES == 1) {
+        switch (radius) {
+            case 5: return launch_direct<ES, 5>(x, y, images, rule, std_eff, taps_dev, stream);
+            default: break;
+        }
+    }
+    set_error("blur_direct: radius %d not supported", radius);
+    return BGAN_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+// Measured on B200 (256 x 3 x 128 x 128, us per launch; tensor-core kernel: 28 NCHW / 57 NHWC for every radius):
+//   NCHW  r = 1 .. 3: 18.3 - 18.6 (a device-to-device copy of the same bytes takes 18.7),  r = 4: 21.0,  r = 5: 26.8,  r = 6: 30.0
+//   NHWC  r = 2: 23.0,  r = 3: 24.5,  r = 4: 30.3
+constexpr int kDirectMaxRadius1 = 5, kDirectMaxRadius3 = 4;
+
+// planes: N * C planes of 128 x 128 (ES == 1) or N images of 128 x 384 interleaved floats (ES == 3)
+bool blur_direct_eligible(int planes, int H, int Wc, int ES, int radius, const float* x, const float* y) {
+    const char* off = getenv("BGAN_BLUR_NO_DIRECT");
+    if (off && atoi(off)) return false;
+    const char* max_r = getenv("BGAN_BLUR_DIRECT_MAX_R");
+    const int cap = ES == 1 ? kDirectMaxRadius1 : kDirectMaxRadius3;
+    const int rmax = max_r ? std::min(atoi(max_r), cap) : cap;
+    return (ES == 1 || ES == 3) && H == kD && Wc == kD * ES && planes > 0 && radius >= 1 && radius <= rmax &&
+           reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 && direct_encode_fn() != nullptr;
+}
+
+int blur_direct_launch(const float* x, float* y, int planes, int es, int radius, int rule, float std_eff, const float* taps_dev,
+                       cudaStream_t stream) {
+    return es == 1 ? launch_direct_r<1>(x, y, planes, radius, rule, std_eff, taps_dev, stream)
+                   : launch_direct_r<3>(x, y, planes, radius, rule, std_eff, taps_dev, stream);
+}
+
+}  // namespace bgan

@@ -137,7 +137,7 @@ def test_tma_and_plain_staging_agree_bitwise():
     from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
 
     x = _dev(uniform_pm1(8, (5, 3, 128, 128)))
-    os.environ["BGAN_BLUR_NO_TC"] = "1"  # this test is about the CUDA-core tile kernel
+    os.environ["BGAN_BLUR_NO_TC"] = os.environ["BGAN_BLUR_NO_DIRECT"] = "1"  # this test is about the CUDA-core tile kernel
     for std in (0.5, 2.0, 5.0, 23.0):
         mod = GaussianBlur(std).cuda()
         os.environ.pop("BGAN_BLUR_NO_TMA", None)
@@ -151,6 +151,7 @@ def test_tma_and_plain_staging_agree_bitwise():
             os.environ.pop("BGAN_BLUR_NO_TMA", None)
             if std == 23.0:
                 os.environ.pop("BGAN_BLUR_NO_TC", None)
+                os.environ.pop("BGAN_BLUR_NO_DIRECT", None)
         assert path_tma == 1 and path_plain == 2
         assert torch.equal(y_tma, y_plain)
 
@@ -162,13 +163,14 @@ def test_tilings_agree(th, tw):
     x = _dev(uniform_pm1(9, (3, 2, 128, 128)))
     for std in (1.0, 5.0):
         mod = GaussianBlur(std).cuda()
-        os.environ["BGAN_BLUR_NO_TC"] = "1"
+        os.environ["BGAN_BLUR_NO_TC"] = os.environ["BGAN_BLUR_NO_DIRECT"] = "1"
         try:
             want = mod(x)
             os.environ["BGAN_BLUR_TH"], os.environ["BGAN_BLUR_TW"] = str(th), str(tw)
             got = mod(x)
         finally:
             os.environ.pop("BGAN_BLUR_TH", None), os.environ.pop("BGAN_BLUR_TW", None), os.environ.pop("BGAN_BLUR_NO_TC", None)
+            os.environ.pop("BGAN_BLUR_NO_DIRECT", None)
         assert_close(got, want.cpu().numpy(), "tile %dx%d std=%g" % (th, tw, std))
 
 
@@ -244,12 +246,13 @@ def test_ones_image_border_profile_and_errors():
 
 
 @pytest.mark.parametrize("std", [0.01, 0.5, 2.0, 5.0, 12.0, 23.0, 40.0])
-def test_tensor_core_path_matches_oracle_and_fma_path(std):
+def test_tensor_core_path_matches_oracle_and_fma_path(std, monkeypatch):
     """128 x 128 planes run on tcgen05 (fp16 split, fp32 accumulate in TMEM): same 1e-5 bar, any input magnitude."""
     from blurred_gan_b200 import ops
     from blurred_gan_b200.gaussian_blur import blur_images
     from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
 
+    monkeypatch.setenv("BGAN_BLUR_NO_DIRECT", "1")  # small radii would otherwise take the FFMA path (blur_direct.cu)
     x = uniform_pm1(20, (7, 3, 128, 128))
     x[1] *= 1e-6   # tiny plane magnitudes (gradients)
     x[2] *= 3e4    # beyond fp16 range without the per-plane power-of-two scale
@@ -276,11 +279,12 @@ def test_tensor_core_path_matches_oracle_and_fma_path(std):
 
 
 @pytest.mark.parametrize("std", [0.5, 3.0, 23.0])
-def test_tensor_core_path_nhwc(std):
+def test_tensor_core_path_nhwc(std, monkeypatch):
     """NHWC 128 x 128 x 3 (the layout of the reference's Keras layer): TMA deinterleaves with element stride 3."""
     from blurred_gan_b200 import ops
     from blurred_gan_b200.gaussian_blur import GaussianBlur2D
 
+    monkeypatch.setenv("BGAN_BLUR_NO_DIRECT", "1")
     x = uniform_pm1(30, (5, 128, 128, 3))
     x[1] *= 1e-5
     layer = GaussianBlur2D(std).cuda()
@@ -295,3 +299,65 @@ def test_tensor_core_path_nhwc(std):
     assert_close(xd.grad, bo.blur_images_tf_ref(g, std), "NHWC tensor-core backward std=%g" % std)
     x1 = uniform_pm1(32, (4, 128, 128, 1))
     assert_close(layer(_dev(x1)), bo.blur_images_tf_ref(x1, std), "NHWC C=1 std=%g" % std)
+
+
+@pytest.mark.parametrize("std", [0.01, 0.3, 0.5, 0.7, 1.0, 1.3])
+def test_direct_path_small_radius(std):
+    """128 x 128 images with radius <= 4 (the small-sigma end of the annealing) run on the FFMA kernel of blur_direct.cu:
+    both layouts, both tap rules, forward and backward, any plane magnitude."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(40, (5, 3, 128, 128))
+    x[1] *= 1e-6
+    x[2] *= 3e4
+    x[3, 0] = 0.0
+    mod = GaussianBlur(std).cuda()
+    k_torch, r_torch = bo.torch_rule_plan(std, 128, 128)
+    xd = _dev(x).requires_grad_(True)
+    y = mod(xd)
+    assert ops.last_blur_path() == (5 if r_torch <= 4 else 4)
+    want = bo.gaussian_blur_torch_ref(x, std)
+    for n in range(x.shape[0]):
+        assert_close(y[n], want[n], "direct path NCHW image %d std=%g" % (n, std))
+    g = uniform_pm1(41, x.shape)
+    y.backward(_dev(g))
+    assert_close(xd.grad, bo.gaussian_blur_torch_ref(g, std), "direct path NCHW backward std=%g" % std)
+    # NHWC, tf rule (k = floor(6 std) + 1): radius 1 .. 4 for std <= 1.3
+    xh = uniform_pm1(42, (6, 128, 128, 3))
+    xh[4] *= 1e-4
+    layer = GaussianBlur2D(std).cuda()
+    xhd = _dev(xh).requires_grad_(True)
+    yh = layer(xhd)
+    assert ops.last_blur_path() == 5
+    wanth = bo.blur_images_tf_ref(xh, std)
+    for n in range(xh.shape[0]):
+        assert_close(yh[n], wanth[n], "direct path NHWC image %d std=%g" % (n, std))
+    gh = uniform_pm1(43, xh.shape)
+    yh.backward(_dev(gh))
+    assert_close(xhd.grad, bo.blur_images_tf_ref(gh, std), "direct path NHWC backward std=%g" % std)
+    # one image / odd image counts (NHWC units are half images)
+    x1 = uniform_pm1(44, (1, 128, 128, 3))
+    assert_close(layer(_dev(x1)), bo.blur_images_tf_ref(x1, std), "direct path NHWC single image std=%g" % std)
+    x1c = uniform_pm1(45, (3, 128, 128, 1))
+    assert_close(layer(_dev(x1c)), bo.blur_images_tf_ref(x1c, std), "direct path NHWC C=1 std=%g" % std)
+
+
+def test_direct_path_explicit_asymmetric_taps():
+    """Explicit taps on the direct path: correlation orientation in both passes, adjoint = reversed taps."""
+    from blurred_gan_b200 import ops
+
+    asym = np.array([0.05, 0.1, 0.15, 0.3, 0.25, 0.1, 0.05], dtype=np.float32)  # radius 3
+    x_np = uniform_pm1(46, (4, 3, 128, 128))
+    x = _dev(x_np).requires_grad_(True)
+    y = ops.blur2d_taps(x, torch.from_numpy(asym).cuda(), ops.LAYOUT_NCHW)
+    assert ops.last_blur_path() == 5
+    assert_close(y, bo.blur_nchw(x_np, asym), "direct path, asymmetric taps")
+    g_np = uniform_pm1(47, x_np.shape)
+    y.backward(_dev(g_np))
+    assert_close(x.grad, bo.blur_nchw(g_np, asym[::-1].copy()), "direct path, adjoint of asymmetric taps")
+    xh_np = uniform_pm1(48, (3, 128, 128, 3))
+    yh = ops.blur2d_taps(_dev(xh_np), torch.from_numpy(asym).cuda(), ops.LAYOUT_NHWC)
+    assert ops.last_blur_path() == 5
+    assert_close(yh, bo.blur_nhwc(xh_np, asym), "direct path NHWC, asymmetric taps")
