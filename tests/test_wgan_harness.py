@@ -179,8 +179,9 @@ def test_swd_metric_on_device_tensors():
         m.update_state(torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1, torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1)
     res = m.result()
     assert len(res) == len(m.metric_names()) and all(math.isfinite(v) and v > 0 for v in res)
-    same = SWDMetric((3, 64, 64))
-    x = torch.rand(16, 3, 64, 64, device="cuda")
-    same.update_state(x, x)
+    # a set with different local statistics (smooth ramps + a little noise) is further away than a second noise set
+    far = SWDMetric((3, 64, 64))
+    ramp = torch.linspace(-1, 1, 64, device="cuda").view(1, 1, 1, 64).expand(32, 3, 64, 64)
+    far.update_state(torch.rand(32, 3, 64, 64, device="cuda") * 2 - 1, ramp + 0.05 * torch.randn(32, 3, 64, 64, device="cuda"))
     np.random.seed(0)
-    assert same.result()[-1] < res[-1]
+    assert far.result()[0] > 3 * res[0]
