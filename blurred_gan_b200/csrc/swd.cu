@@ -80,44 +80,57 @@ __global__ void pyr_up_kernel(const float* __restrict__ x, const float* __restri
     }
 }
 
-// desc[m, c, i, j] = level[m / per_image, c, py[m] + j - half, px[m] + i - half]; per-channel sum / sum-of-squares
+// desc[m, c, i, j] = level[m / per_image, c, py[m] + j - half, px[m] + i - half]; per-channel sum / sum-of-squares.
+// One warp per descriptor (grid-stride): the lanes walk the C * nhood^2 floats of the descriptor, so the output row is
+// written coalesced and all index arithmetic is 32-bit.  The channel statistics are accumulated in fp64 per thread,
+// reduced per warp and per CTA in shared memory, and only then added to the global sums: six atomics per CTA (one atomic
+// per warp and statistic made this kernel 75 us per minibatch, all of it contention on six addresses).
 template <int MAXC>
-__global__ void extract_kernel(const float* __restrict__ level, int C, int h, int w, const int32_t* __restrict__ px,
-                               const int32_t* __restrict__ py, int per_image, int nhood, int64_t n_desc,
-                               float* __restrict__ out, double* __restrict__ sums) {
+__global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ level, int C, int h, int w, const int32_t* __restrict__ px,
+                                                      const int32_t* __restrict__ py, int per_image, int nhood, int64_t n_desc,
+                                                      float* __restrict__ out, double* __restrict__ sums) {
+    __shared__ double s_part[8][2 * MAXC];
     const int half = nhood / 2;
     const int per_chan = nhood * nhood;
     const int dlen = C * per_chan;
-    const int64_t total = n_desc * dlen;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     double s1[MAXC], s2[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) s1[c] = s2[c] = 0.0;
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t m = idx / dlen;
-        const int k = static_cast<int>(idx - m * dlen);
-        const int c = k / per_chan;
-        const int ij = k - c * per_chan;
-        const int i = ij / nhood, j = ij - i * nhood;
-        const int64_t img = m / per_image;
-        const int row = __ldg(py + m) + j - half;
-        const int col = __ldg(px + m) + i - half;
-        const float v = __ldg(level + ((img * C + c) * h + row) * static_cast<int64_t>(w) + col);
-        out[idx] = v;
+    for (int64_t m = static_cast<int64_t>(blockIdx.x) * warps + warp; m < n_desc; m += static_cast<int64_t>(gridDim.x) * warps) {
+        const int y0 = __ldg(py + m) - half, x0 = __ldg(px + m) - half;
+        const float* img = level + (m / per_image) * C * static_cast<int64_t>(h) * w;
+        float* dst = out + m * dlen;
+        for (int k = lane; k < dlen; k += 32) {
+            const int c = k / per_chan;
+            const int ij = k - c * per_chan;
+            const int i = ij / nhood, j = ij - i * nhood;
+            const float v = __ldg(img + (c * h + y0 + j) * w + x0 + i);
+            dst[k] = v;
+            const double dv = static_cast<double>(v);
 #pragma unroll
-        for (int cc = 0; cc < MAXC; ++cc)
-            if (cc == c) {
-                s1[cc] += static_cast<double>(v);
-                s2[cc] += static_cast<double>(v) * static_cast<double>(v);
-            }
+            for (int cc = 0; cc < MAXC; ++cc)
+                if (cc == c) {
+                    s1[cc] += dv;
+                    s2[cc] += dv * dv;
+                }
+        }
     }
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
-        if (c >= C) break;
         const double a = warp_sum(s1[c]), b = warp_sum(s2[c]);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(sums + c, a);
-            atomicAdd(sums + C + c, b);
+        if (lane == 0) {
+            s_part[warp][c] = a;
+            s_part[warp][MAXC + c] = b;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * MAXC) {
+        const int c = threadIdx.x % MAXC, which = threadIdx.x / MAXC;
+        if (c < C) {
+            double t = 0.0;
+            for (int q = 0; q < warps; ++q) t += s_part[q][threadIdx.x];
+            atomicAdd(sums + which * C + c, t);
         }
     }
 }
@@ -253,8 +266,10 @@ extern "C" int bgan_swd_extract_f32(const float* level, int n, int c, int h, int
                  BGAN_E_BADARG, "bgan_swd_extract_f32: bad shape (n=%d c=%d h=%d w=%d nhood=%d)", n, c, h, w, nhood);
     const int64_t n_desc = static_cast<int64_t>(n) * nhoods_per_image;
     const int64_t total = n_desc * c * nhood * nhood;
-    extract_kernel<4><<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(level, c, h, w, px, py, nhoods_per_image,
-                                                                                          nhood, n_desc, desc_out, sums);
+    (void)total;
+    const int64_t ctas = std::min<int64_t>(ceil_div64(n_desc, 8), 8 * static_cast<int64_t>(device_sm_count()));
+    extract_kernel<4><<<static_cast<unsigned>(ctas), 256, 0, static_cast<cudaStream_t>(stream)>>>(level, c, h, w, px, py, nhoods_per_image,
+                                                                                              nhood, n_desc, desc_out, sums);
     BGAN_LAUNCH_OK();
     return 0;
 }

@@ -179,9 +179,16 @@ def test_swd_metric_on_device_tensors():
         m.update_state(torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1, torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1)
     res = m.result()
     assert len(res) == len(m.metric_names()) and all(math.isfinite(v) and v > 0 for v in res)
-    # a set with different local statistics (smooth ramps + a little noise) is further away than a second noise set
-    far = SWDMetric((3, 64, 64))
-    ramp = torch.linspace(-1, 1, 64, device="cuda").view(1, 1, 1, 64).expand(32, 3, 64, 64)
-    far.update_state(torch.rand(32, 3, 64, 64, device="cuda") * 2 - 1, ramp + 0.05 * torch.randn(32, 3, 64, 64, device="cuda"))
+    # the metric is the API fed with the same minibatches under the same numpy seed
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    torch.manual_seed(0)
+    batches = [(torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1, torch.rand(16, 3, 64, 64, device="cuda") * 2 - 1) for _ in range(2)]
     np.random.seed(0)
-    assert far.result()[0] > 3 * res[0]
+    api = sw.API((3, 64, 64))
+    for mode, k in (("reals", 0), ("fakes", 1)):
+        api.begin(mode)
+        for b in batches:
+            api.feed(mode, b[k])
+        want = api.end(mode)
+    assert res == pytest.approx(want, rel=1e-6)
