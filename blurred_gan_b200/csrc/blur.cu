@@ -33,6 +33,11 @@ namespace bgan {
 bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, const float* x, const float* y);
 int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream);
 
+// blur_axis.cu: two-pass tensor-core path for large planes and wide blurs
+bool blur_axis_eligible(int planes, int H, int W, int ES, int radius, const float* x, const float* y);
+size_t blur_axis_workspace_bytes(int planes, int H, int W);
+int blur_axis_launch(const float* x, float* y, int planes, int H, int W, int rule, float std_eff, int radius, const float* taps_dev, void* ws,
+                     size_t ws_bytes, cudaStream_t stream);
 // blur_direct.cu: FFMA path for 128 x 128 images and radius <= 4
 bool blur_direct_eligible(int planes, int H, int Wc, int ES, int radius, const float* x, const float* y);
 int blur_direct_launch(const float* x, float* y, int planes, int es, int radius, int rule, float std_eff, const float* taps_dev,
@@ -541,6 +546,9 @@ extern "C" int bgan_blur_taps_f32(int rule, float std_eff, int radius, float* ta
 extern "C" size_t bgan_blur2d_workspace_bytes(int n, int c, int height, int width, int layout, int radius) {
     Geometry g;
     if (!geometry(n, c, height, width, layout, &g) || radius < 0) return 0;
+    // (pointer alignment is not known here: 16-byte aligned dummies stand for "aligned like a fresh allocation")
+    const float* aligned = reinterpret_cast<const float*>(uintptr_t(256));
+    if (blur_axis_eligible(g.planes, g.H, g.Wc, g.ES, radius, aligned, aligned)) return blur_axis_workspace_bytes(g.planes, g.H, g.Wc);
     Plan fused = choose_plan(g.H, g.Wc, g.ES, radius, radius);
     if (fused.ok) return 0;
     return static_cast<size_t>(g.planes) * g.H * g.Wc * sizeof(float);
@@ -562,6 +570,11 @@ extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int heigh
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     bool tma = false;
 
+    if (blur_axis_eligible(g.planes, g.H, g.Wc, g.ES, radius, x, y) && ws != nullptr &&
+        ws_bytes >= blur_axis_workspace_bytes(g.planes, g.H, g.Wc) && reinterpret_cast<uintptr_t>(ws) % 16 == 0) {
+        g_last_path = 6;
+        return blur_axis_launch(x, y, g.planes, g.H, g.Wc, rule, std_eff, radius, taps_device, ws, ws_bytes, stream);
+    }
     if (blur_direct_eligible(g.planes, g.H, g.Wc, g.ES, radius, x, y)) {
         g_last_path = 5;
         return blur_direct_launch(x, y, g.planes, g.ES, radius, rule, std_eff, taps_device, stream);

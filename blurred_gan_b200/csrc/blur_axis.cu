@@ -1,0 +1,405 @@
+// Tensor-core blur for planes larger than 128 x 128 (BASELINE configs[3]: 1024 x 1024, radius up to 192).
+//
+// One kernel, applied twice:   out[p][j][i] = sum_k T[j][k] in[p][i][k],   T[j][k] = tap[k - j + r]  (|k - j| <= r)
+// i.e. "blur along the contiguous axis and write the result transposed".  Pass 1 turns X[h][w] into Z^T[w'][h]
+// (scratch), pass 2 turns Z^T[w'][h] into Y[h'][w']: both passes read rows that are contiguous along the axis they
+// blur -- the natural K-major B operand -- and both stores are 128-byte row segments.  With the CUDA-core tile kernel the
+// wide blurs of configs[3] cost 2 (2r + 1) = 770 FMAs per pixel; here the cost per 128 x 128 output tile is
+// (2 nb + 1) x 24 tcgen05.mma, nb = ceil(r / 128) <= 2.
+//
+// Tile: 128 outputs j (accumulator rows) x 128 input rows i (accumulator columns), accumulated over the 2 nb + 1 blocks
+// of 128 k that the band of T touches.  A = T block (offset d = L - J): core matrices of a Toeplitz block only depend on
+// 16 d + kchunk - rowgroup, so all 2 nb + 1 blocks are views (LBO = SBO = 128 B descriptors, row groups reversed, see
+// blur_tc.cu) of one strip of 32 nb + 31 core matrices.  B = the fp32 block of `in`, staged by TMA (out-of-bounds zero
+// fill = the reference's zero padding), scaled per row by a power of two (row maxima come from a tiny pre-pass for pass 1
+// and from pass 1's epilogue for pass 2) and split into fp16 hi | lo by the compute warps.  fp32 parity as in blur_tc.cu:
+// A B ~= A1 B1 + 2^-11 (A1 B2 + A2 B1), here with one TMEM accumulator for the main and one for the cross terms, combined
+// in the epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "taps.cuh"
+
+namespace bgan {
+namespace {
+
+constexpr int kB = 128;                        // block edge
+constexpr int kAxThreads = 512;                // compute threads (16 warps)
+constexpr int kAxWarps = kAxThreads / 32;
+constexpr int kAxCta = kAxThreads + 32;        // + the MMA-issuing warp
+constexpr int kAxMaxNb = 2;                    // radius <= 256
+constexpr uint32_t kALBO = 144, kASBO = 16 * kALBO, kATile = 16 * kASBO;  // padded K-major operand tile (see blur_tc.cu)
+constexpr uint32_t kAStage = kB * kB * 4;      // 65536
+constexpr uint32_t kAOffStage = 0;             // two staging blocks
+constexpr uint32_t kAOffX1 = 2 * kAStage;      // X hi tile (the raw taps live here until the first conversion)
+constexpr uint32_t kAOffX2 = kAOffX1 + kATile;
+constexpr uint32_t kAStripBytes = 12288;       // (32 * 2 + 31) core matrices x 128 B = 12160
+constexpr uint32_t kAOffS1 = kAOffX2 + kATile;
+constexpr uint32_t kAOffS2 = kAOffS1 + kAStripBytes;
+constexpr uint32_t kAOffMisc = kAOffS2 + kAStripBytes;  // s_scale[128], s_inv[128], barriers
+constexpr uint32_t kASmem = kAOffMisc + 1024 + 256;
+constexpr uint32_t kAIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // kind::f16, D = f32, M = N = 128, K-major
+constexpr int kARev = 0x78;
+
+struct AxisArgs {
+    float* out;               // [planes][K][I]
+    const float* rowmax_in;   // [planes][I]: max |in| over each row
+    float* rowmax_out;        // [planes][K] or nullptr: max |out| over each output row (accumulated with atomicMax)
+    int I, K, planes;
+    int tiles_i, tiles_j;
+    int nb;                   // ceil(radius / 128)
+    int rule;
+    float std_eff;
+    int radius;
+    const float* taps_dev;
+};
+
+__device__ __forceinline__ uint32_t ax_tile_off(int row, int k) { return (row >> 3) * kASBO + (k >> 3) * kALBO + (row & 7) * 16 + (k & 7) * 2; }
+__device__ __forceinline__ uint64_t ax_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) | (static_cast<uint64_t>(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void ax_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(kAIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void ax_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ax_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ax_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ax_ld32(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+          "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+          "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void ax_ld_wait(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                   "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]),
+                   "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]),
+                   "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void ax_split2(float a, float b, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hi);
+    lo = __floats2half2_rn((a - back.x) * 2048.0f, (b - back.y) * 2048.0f);
+}
+
+// max |x| of every row of a [rows][len] array (one warp per row)
+__global__ void rowmax_kernel(const float* __restrict__ x, int64_t rows, int len, float* __restrict__ rowmax) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const float4* p = reinterpret_cast<const float4*>(x + row * len);
+    float m = 0.0f;
+    for (int i = lane; i < len / 4; i += 32) {
+        const float4 v = __ldg(p + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) rowmax[row] = m;
+}
+
+// Block t of this CTA's work list: tile = first + (t / nblk) * stride, L-offset d = t % nblk - nb.
+struct BlockCoord {
+    int plane, ib, jb, d;
+    bool valid;
+};
+__device__ __forceinline__ BlockCoord block_coord(const AxisArgs& a, int t, int first, int stride, int n_tiles) {
+    const int nblk = 2 * a.nb + 1;
+    const int tile = first + (t / nblk) * stride;
+    BlockCoord c;
+    c.valid = tile < n_tiles;
+    c.d = t % nblk - a.nb;
+    c.jb = tile % a.tiles_j;
+    c.ib = (tile / a.tiles_j) % a.tiles_i;
+    c.plane = tile / (a.tiles_j * a.tiles_i);
+    return c;
+}
+
+__global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* s_g = reinterpret_cast<float*>(smem + kAOffX1);  // taps (<= 513), only until the strip is built
+    float* s_scale = reinterpret_cast<float*>(smem + kAOffMisc);  // [128] per input row of the tile
+    float* s_inv = s_scale + kB;                                  // [128]
+    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kAOffMisc + 1024);  // [2]
+    uint64_t* mbar_mma = mbar_tma + 2;  // one phase per block: its MMAs are complete (X tiles free; after the last block: D valid)
+    double* s_red = reinterpret_cast<double*>(mbar_tma + 3);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 4);
+    const uint32_t sbase = smem_u32(smem);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n_tiles = a.planes * a.tiles_i * a.tiles_j;
+    const int nblk = 2 * a.nb + 1;
+    const int my_tiles = (n_tiles - first + stride - 1) / stride;
+    const int n_blocks = my_tiles * nblk;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(mbar_tma + 0, 1);
+        mbar_init(mbar_tma + 1, 1);
+        mbar_init(mbar_mma, 1);
+        mbar_fence_init();
+    }
+    if (warp == kAxWarps) {  // TMEM: D_main = [0, 128), D_cross = [128, 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (a.rule == BGAN_RULE_EXPLICIT) asm volatile("griddepcontrol.wait;" ::: "memory");
+    normalised_taps(a.rule, a.std_eff, a.radius, a.taps_dev, s_g, s_red);  // (ends with __syncthreads)
+    // ---- the strip: core matrix m = 16 (d + nb) + kchunk + rowgroup', row rho, holds taps t0 .. t0 + 7,
+    //      t0 = 8 (m - 16 nb - 15) - rho + r  (zero outside [0, 2r]) ----
+    {
+        const int n_taps = 2 * a.radius + 1, mats = 32 * a.nb + 31;
+        for (int j = tid; j < mats * 32; j += kAxCta) {
+            const int m = j >> 5, rho = (j >> 2) & 7, e = j & 3;
+            const int ta = 8 * (m - 16 * a.nb - 15) - rho + a.radius + 2 * e, tb = ta + 1;
+            __half2 hi, lo;
+            ax_split2((ta >= 0 && ta < n_taps) ? s_g[ta] : 0.0f, (tb >= 0 && tb < n_taps) ? s_g[tb] : 0.0f, hi, lo);
+            *reinterpret_cast<__half2*>(smem + kAOffS1 + m * 128 + rho * 16 + e * 4) = hi;
+            *reinterpret_cast<__half2*>(smem + kAOffS2 + m * 128 + rho * 16 + e * 4) = lo;
+        }
+    }
+    fence_proxy_async();
+    ax_fence_before();
+    __syncthreads();
+    ax_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t d_main = tmem, d_cross = tmem + 128;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // `in` may be written, `out` may still be read by the previous grid
+
+    auto issue_load = [&](int t) {  // (one thread) block t -> staging[t & 1]
+        const BlockCoord c = block_coord(a, t, first, stride, n_tiles);
+        mbar_arrive_expect_tx(mbar_tma + (t & 1), kAStage);
+        tma_load_3d(smem + kAOffStage + (t & 1) * kAStage, &tmap, mbar_tma + (t & 1), (c.jb + c.d) * kB, c.ib * kB, c.plane);
+    };
+
+    if (warp == kAxWarps) {
+        // ================= MMA issuer =================================================================
+        if (lane == 0) {
+            issue_load(0);
+            if (n_blocks > 1) issue_load(1);
+        }
+        __syncwarp();
+        for (int t = 0; t < n_blocks; ++t) {
+            named_bar_sync(1, kAxThreads + 32);  // X tiles of block t written
+            if (lane == 0) {
+                ax_fence_after();
+                const int l = t % nblk;  // d + nb
+                const uint64_t a1 = ax_desc(sbase + kAOffS1 + l * 16 * 128, 128, 128), a2 = ax_desc(sbase + kAOffS2 + l * 16 * 128, 128, 128);
+                const uint64_t b1 = ax_desc(sbase + kAOffX1, kALBO, kASBO), b2 = ax_desc(sbase + kAOffX2, kALBO, kASBO);
+                const uint32_t acc0 = l > 0;  // the first block of a tile overwrites the accumulators
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ax_mma(d_cross, a1 + k * 16, b2 + k * 18, acc0 | (k > 0));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ax_mma(d_cross, a2 + k * 16, b1 + k * 18, 1);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ax_mma(d_main, a1 + k * 16, b1 + k * 18, acc0 | (k > 0));
+                ax_commit(mbar_mma);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= compute warps ==============================================================
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const int col_base = (warp >> 2) * 32;
+        const int jl = ((warp & 3) * 32 + lane) ^ kARev;  // output position held by this thread's accumulator row
+        for (int t = 0; t < n_blocks; ++t) {
+            const BlockCoord c = block_coord(a, t, first, stride, n_tiles);
+            const int l = t % nblk;
+            if (l == 0) {  // new tile: row scales (previous tile's epilogue is over: it ended with a barrier)
+                if (tid < kB) {
+                    const int i = c.ib * kB + tid;
+                    const float m = i < a.I ? __ldg(a.rowmax_in + static_cast<size_t>(c.plane) * a.I + i) : 0.0f;
+                    int eb = (__float_as_int(m) >> 23) & 0xff;
+                    eb = min(max(eb, 13), 254);
+                    s_scale[tid] = __int_as_float((266 - eb) << 23);  // max |row| -> [2^12, 2^13)
+                    s_inv[tid] = __int_as_float((eb - 12) << 23);
+                }
+                named_bar_sync(2, kAxThreads);
+            }
+            // ---- staging -> registers ----
+            mbar_wait(mbar_tma + (t & 1), (t >> 1) & 1);
+            const float* stage = reinterpret_cast<const float*>(smem + kAOffStage + (t & 1) * kAStage);
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(stage + (q * kAxThreads + tid) * 4);
+            named_bar_sync(2, kAxThreads);  // staging drained
+            if (tid == 0 && t + 2 < n_blocks) issue_load(t + 2);
+            if (t > 0) mbar_wait(mbar_mma, (t - 1) & 1);  // MMAs of block t - 1 complete: X tiles free
+            // ---- registers -> X hi | lo tiles (row = i, K = k) ----
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int f = q * kAxThreads + tid;
+                const int h = f >> 5, w = (f & 31) << 2;
+                const float sc = s_scale[h];
+                __half2 hi[2], lo[2];
+                ax_split2(v[q].x * sc, v[q].y * sc, hi[0], lo[0]);
+                ax_split2(v[q].z * sc, v[q].w * sc, hi[1], lo[1]);
+                const uint32_t off = ax_tile_off(h, w);
+                *reinterpret_cast<uint2*>(smem + kAOffX1 + off) = *reinterpret_cast<uint2*>(hi);
+                *reinterpret_cast<uint2*>(smem + kAOffX2 + off) = *reinterpret_cast<uint2*>(lo);
+            }
+            fence_proxy_async();
+            ax_fence_before();
+            named_bar_sync(1, kAxThreads + 32);  // -> MMAs of block t
+            if (l == nblk - 1) {
+                // ---- epilogue of the tile: out[j][i] = (D_main + 2^-11 D_cross) / scale_i ----
+                mbar_wait(mbar_mma, t & 1);
+                ax_fence_after();
+                float dm[32], dc[32];
+                ax_ld32(d_main + lane_base + col_base, dm);
+                ax_ld32(d_cross + lane_base + col_base, dc);
+                ax_ld_wait(dm);
+                ax_ld_wait(dc);
+                const int j = c.jb * kB + jl;
+                const int i0 = c.ib * kB + col_base;
+                float mx = 0.0f;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    dm[e] = fmaf(dc[e], 1.0f / 2048.0f, dm[e]) * s_inv[col_base + e];
+                    mx = fmaxf(mx, fabsf(dm[e]));
+                }
+                if (j < a.K) {
+                    float* dst = a.out + (static_cast<size_t>(c.plane) * a.K + j) * a.I + i0;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        if (i0 + e < a.I) __stcs(reinterpret_cast<float4*>(dst + e), make_float4(dm[e], dm[e + 1], dm[e + 2], dm[e + 3]));
+                    if (a.rowmax_out != nullptr)
+                        atomicMax(reinterpret_cast<int*>(a.rowmax_out + static_cast<size_t>(c.plane) * a.K + j), __float_as_int(mx));
+                }
+                ax_fence_before();
+                named_bar_sync(2, kAxThreads);  // accumulators and scales are free for the next tile
+            }
+        }
+    }
+    ax_fence_before();
+    __syncthreads();
+    if (warp == kAxWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn axis_encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// one pass: in [planes][I][K] -> out [planes][K][I]
+int launch_axis(const float* in, float* out, const float* rowmax_in, float* rowmax_out, int planes, int I, int K, int rule, float std_eff,
+                int radius, const float* taps_dev, cudaStream_t stream) {
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    thread_local bool bound = false;
+    if (!bound) {
+        cudaFree(nullptr);
+        bound = true;
+    }
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(I), static_cast<cuuint64_t>(planes)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 4, static_cast<cuuint64_t>(K) * I * 4};
+    const cuuint32_t box[3] = {kB, kB, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult res = axis_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
+    thread_local int attr_dev = -1;
+    int dev = 0;
+    BGAN_CUDA_OK(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_axis_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kASmem)));
+        attr_dev = dev;
+    }
+    AxisArgs a{};
+    a.out = out;
+    a.rowmax_in = rowmax_in;
+    a.rowmax_out = rowmax_out;
+    a.I = I;
+    a.K = K;
+    a.planes = planes;
+    a.tiles_i = ceil_div(I, kB);
+    a.tiles_j = ceil_div(K, kB);
+    a.nb = ceil_div(radius, kB);
+    a.rule = rule;
+    a.std_eff = std_eff;
+    a.radius = radius;
+    a.taps_dev = taps_dev;
+    const int64_t n_tiles = static_cast<int64_t>(planes) * a.tiles_i * a.tiles_j;
+    BGAN_REQUIRE(n_tiles < (int64_t(1) << 28), BGAN_E_BADARG, "blur_axis: too many tiles");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(std::min<int64_t>(n_tiles, device_sm_count())));
+    cfg.blockDim = dim3(kAxCta);
+    cfg.dynamicSmemBytes = kASmem;
+    cfg.stream = stream;
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_axis_tc_kernel, a, tmap));
+    return 0;
+}
+
+}  // namespace
+
+// planes of H x W floats, contiguous (NCHW, or NHWC with one channel)
+bool blur_axis_eligible(int planes, int H, int W, int ES, int radius, const float* x, const float* y) {
+    const char* off = getenv("BGAN_BLUR_NO_AXIS_TC");
+    if (off && atoi(off)) return false;
+    const char* min_r = getenv("BGAN_BLUR_AXIS_MIN_R");
+    const int rmin = min_r ? atoi(min_r) : 12;
+    return ES == 1 && planes > 0 && H >= 256 && W >= 256 && H % 4 == 0 && W % 4 == 0 && radius >= rmin && radius <= kAxMaxNb * kB &&
+           reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 && axis_encode_fn() != nullptr;
+}
+
+// scratch: the transposed intermediate plus the two row-maximum arrays
+size_t blur_axis_workspace_bytes(int planes, int H, int W) {
+    const size_t mid = (static_cast<size_t>(planes) * H * W * sizeof(float) + 255) & ~size_t(255);
+    const size_t rm = (static_cast<size_t>(planes) * (H + W) * sizeof(float) + 255) & ~size_t(255);
+    return mid + rm;
+}
+
+int blur_axis_launch(const float* x, float* y, int planes, int H, int W, int rule, float std_eff, int radius, const float* taps_dev, void* ws,
+                     size_t ws_bytes, cudaStream_t stream) {
+    BGAN_REQUIRE(ws && ws_bytes >= blur_axis_workspace_bytes(planes, H, W) && reinterpret_cast<uintptr_t>(ws) % 16 == 0, BGAN_E_WORKSPACE,
+                 "blur_axis: workspace of %zu bytes required, got %zu", blur_axis_workspace_bytes(planes, H, W), ws_bytes);
+    const size_t mid_bytes = (static_cast<size_t>(planes) * H * W * sizeof(float) + 255) & ~size_t(255);
+    float* mid = static_cast<float*>(ws);                                          // Z^T [planes][W][H]
+    float* rm_x = reinterpret_cast<float*>(static_cast<char*>(ws) + mid_bytes);   // [planes][H]
+    float* rm_z = rm_x + static_cast<size_t>(planes) * H;                         // [planes][W]
+    const int64_t rows = static_cast<int64_t>(planes) * H;
+    rowmax_kernel<<<static_cast<unsigned>(ceil_div64(rows * 32, 256)), 256, 0, stream>>>(x, rows, W, rm_x);
+    BGAN_LAUNCH_OK();
+    BGAN_CUDA_OK(cudaMemsetAsync(rm_z, 0, static_cast<size_t>(planes) * W * sizeof(float), stream));
+    int rc = launch_axis(x, mid, rm_x, rm_z, planes, H, W, rule, std_eff, radius, taps_dev, stream);  // blur along W: X[h][w] -> Z^T[w'][h]
+    if (rc) return rc;
+    return launch_axis(mid, y, rm_z, nullptr, planes, W, H, rule, std_eff, radius, taps_dev, stream);  // blur along H: Z^T[w'][h] -> Y[h'][w']
+}
+
+}  // namespace bgan

@@ -76,7 +76,8 @@ int bgan_blur2d_f32(const float* x_device, float* y_device, int n, int c, int he
 
 /* How the last bgan_blur2d_f32 call on this thread was executed: 1 = fused tile kernel with TMA
  * staging, 2 = fused tile kernel with plain loads, 3 = two launches (row pass, column pass), 4 = tcgen05 tensor-core kernel (128 x 128 planes),
- * 5 = direct FFMA kernel for 128 x 128 images with radius <= 5 (NHWC: 4). */
+ * 5 = direct FFMA kernel for 128 x 128 images with radius <= 5 (NHWC: 4), 6 = two-pass tcgen05 kernel for planes of
+ * 256 x 256 and more with radius 12 .. 256 (needs the workspace). */
 int bgan_blur2d_last_path(void);
 
 /* ------------------------------------------------------------------------------------ */

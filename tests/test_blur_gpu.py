@@ -118,18 +118,50 @@ def test_ragged_shapes_both_rules(shape, layout):
 
 
 @pytest.mark.parametrize("std", [8.0, 32.0, 64.0])
-def test_large_image_wide_halo(std):
-    """BASELINE configs[3] shape (1024 x 1024, std up to 64), reduced batch for the CPU oracle."""
+def test_large_image_wide_halo(std, monkeypatch):
+    """BASELINE configs[3] shape (1024 x 1024, std up to 64), reduced batch for the CPU oracle.  NCHW planes run on the
+    two-pass tensor-core kernel (path 6); with it disabled, and for NHWC, on the CUDA-core tile kernel."""
     from blurred_gan_b200 import ops
     from blurred_gan_b200.gaussian_blur import blur_images
     from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
 
     x = uniform_pm1(6, (1, 2, 1024, 1024))
-    assert_close(GaussianBlur(std).cuda()(_dev(x)), bo.gaussian_blur_torch_ref(x, std), "torch 1024 std=%g" % std)
+    x[0, 1] *= 1e-5
+    want = bo.gaussian_blur_torch_ref(x, std)
+    got = GaussianBlur(std).cuda()(_dev(x))
+    assert ops.last_blur_path() == 6
+    for c in range(2):
+        assert_close(got[0, c], want[0, c], "torch 1024 plane %d std=%g (tensor-core axis passes)" % (c, std))
+    monkeypatch.setenv("BGAN_BLUR_NO_AXIS_TC", "1")
+    assert_close(GaussianBlur(std).cuda()(_dev(x))[0, 0], want[0, 0], "torch 1024 std=%g (tile kernel)" % std)
     if std >= 64.0:
         assert ops.last_blur_path() == 3  # row pass + column pass through scratch
+    monkeypatch.delenv("BGAN_BLUR_NO_AXIS_TC")
     xh = uniform_pm1(7, (1, 1024, 1024, 3))
     assert_close(blur_images(_dev(xh), std), bo.blur_images_tf_ref(xh, std), "tf NHWC 1024 std=%g" % std)
+
+
+@pytest.mark.parametrize("shape,std", [((2, 1, 256, 256), 6.0), ((1, 3, 300, 260), 9.0), ((1, 2, 512, 384), 40.0), ((3, 1, 260, 516), 20.0)])
+def test_axis_tensor_core_path_ragged_planes(shape, std):
+    """Planes that are not multiples of the 128 x 128 tile, both tap rules, forward and backward, asymmetric explicit taps."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import blur_images
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(50, shape)
+    x[0, 0, :, : shape[3] // 2] *= 1e-4  # rows and columns of very different magnitude
+    xd = _dev(x).requires_grad_(True)
+    y = GaussianBlur(std).cuda()(xd)
+    assert ops.last_blur_path() == 6
+    assert_close(y, bo.gaussian_blur_torch_ref(x, std), "axis path torch rule %s std=%g" % (shape, std))
+    g = uniform_pm1(51, shape)
+    y.backward(_dev(g))
+    assert_close(xd.grad, bo.gaussian_blur_torch_ref(g, std), "axis path backward %s std=%g" % (shape, std))
+    assert_close(blur_images(_dev(x), std), bo.blur_images_tf_ref(x, std), "axis path tf rule %s std=%g" % (shape, std))
+    asym = np.linspace(0.01, 0.05, 33).astype(np.float32)  # radius 16, not symmetric
+    ya = ops.blur2d_taps(_dev(x), torch.from_numpy(asym).cuda(), ops.LAYOUT_NCHW)
+    assert ops.last_blur_path() == 6
+    assert_close(ya, bo.blur_nchw(x, asym), "axis path, asymmetric taps %s" % (shape,))
 
 
 def test_tma_and_plain_staging_agree_bitwise():
