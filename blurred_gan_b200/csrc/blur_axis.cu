@@ -120,20 +120,18 @@ __global__ void rowmax_kernel(const float* __restrict__ x, int64_t rows, int len
     if (lane == 0) rowmax[row] = m;
 }
 
-// Block t of this CTA's work list: tile = first + (t / nblk) * stride, L-offset d = t % nblk - nb.
-struct BlockCoord {
-    int plane, ib, jb, d;
-    bool valid;
+// A tile and the blocks of its band that lie inside the array: l = d + nb in [l0, l1] (blocks that fall entirely outside
+// read zeros only and are skipped; the block d = 0 always exists).
+struct TileCoord {
+    int plane, ib, jb, l0, l1;
 };
-__device__ __forceinline__ BlockCoord block_coord(const AxisArgs& a, int t, int first, int stride, int n_tiles) {
-    const int nblk = 2 * a.nb + 1;
-    const int tile = first + (t / nblk) * stride;
-    BlockCoord c;
-    c.valid = tile < n_tiles;
-    c.d = t % nblk - a.nb;
+__device__ __forceinline__ TileCoord tile_coord(const AxisArgs& a, int tile) {
+    TileCoord c;
     c.jb = tile % a.tiles_j;
     c.ib = (tile / a.tiles_j) % a.tiles_i;
     c.plane = tile / (a.tiles_j * a.tiles_i);
+    c.l0 = max(0, a.nb - c.jb);
+    c.l1 = min(2 * a.nb, a.nb + a.tiles_j - 1 - c.jb);
     return c;
 }
 
@@ -151,9 +149,6 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int first = blockIdx.x, stride = gridDim.x;
     const int n_tiles = a.planes * a.tiles_i * a.tiles_j;
-    const int nblk = 2 * a.nb + 1;
-    const int my_tiles = (n_tiles - first + stride - 1) / stride;
-    const int n_blocks = my_tiles * nblk;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
@@ -190,109 +185,123 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
     const uint32_t d_main = tmem, d_cross = tmem + 128;
     asm volatile("griddepcontrol.wait;" ::: "memory");  // `in` may be written, `out` may still be read by the previous grid
 
-    auto issue_load = [&](int t) {  // (one thread) block t -> staging[t & 1]
-        const BlockCoord c = block_coord(a, t, first, stride, n_tiles);
-        mbar_arrive_expect_tx(mbar_tma + (t & 1), kAStage);
-        tma_load_3d(smem + kAOffStage + (t & 1) * kAStage, &tmap, mbar_tma + (t & 1), (c.jb + c.d) * kB, c.ib * kB, c.plane);
-    };
-
+    // Blocks are numbered u = 0, 1, ... in the order (tile, l); block u uses staging[u & 1] and phase u of mbar_mma.
     if (warp == kAxWarps) {
         // ================= MMA issuer =================================================================
-        if (lane == 0) {
-            issue_load(0);
-            if (n_blocks > 1) issue_load(1);
-        }
-        __syncwarp();
-        for (int t = 0; t < n_blocks; ++t) {
-            named_bar_sync(1, kAxThreads + 32);  // X tiles of block t written
-            if (lane == 0) {
-                ax_fence_after();
-                const int l = t % nblk;  // d + nb
-                const uint64_t a1 = ax_desc(sbase + kAOffS1 + l * 16 * 128, 128, 128), a2 = ax_desc(sbase + kAOffS2 + l * 16 * 128, 128, 128);
-                const uint64_t b1 = ax_desc(sbase + kAOffX1, kALBO, kASBO), b2 = ax_desc(sbase + kAOffX2, kALBO, kASBO);
-                const uint32_t acc0 = l > 0;  // the first block of a tile overwrites the accumulators
+        int u = 0;
+        for (int tile = first; tile < n_tiles; tile += stride) {
+            const TileCoord c = tile_coord(a, tile);
+            for (int l = c.l0; l <= c.l1; ++l, ++u) {
+                named_bar_sync(1, kAxThreads + 32);  // X tiles of block u written
+                if (lane == 0) {
+                    ax_fence_after();
+                    const uint64_t a1 = ax_desc(sbase + kAOffS1 + l * 16 * 128, 128, 128), a2 = ax_desc(sbase + kAOffS2 + l * 16 * 128, 128, 128);
+                    const uint64_t b1 = ax_desc(sbase + kAOffX1, kALBO, kASBO), b2 = ax_desc(sbase + kAOffX2, kALBO, kASBO);
+                    const uint32_t acc0 = l > c.l0;  // the first block of a tile overwrites the accumulators
 #pragma unroll
-                for (int k = 0; k < 8; ++k) ax_mma(d_cross, a1 + k * 16, b2 + k * 18, acc0 | (k > 0));
+                    for (int k = 0; k < 8; ++k) ax_mma(d_cross, a1 + k * 16, b2 + k * 18, acc0 | (k > 0));
 #pragma unroll
-                for (int k = 0; k < 8; ++k) ax_mma(d_cross, a2 + k * 16, b1 + k * 18, 1);
+                    for (int k = 0; k < 8; ++k) ax_mma(d_cross, a2 + k * 16, b1 + k * 18, 1);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) ax_mma(d_main, a1 + k * 16, b1 + k * 18, acc0 | (k > 0));
-                ax_commit(mbar_mma);
+                    for (int k = 0; k < 8; ++k) ax_mma(d_main, a1 + k * 16, b1 + k * 18, acc0 | (k > 0));
+                    ax_commit(mbar_mma);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ================= compute warps ==============================================================
         const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const int col_base = (warp >> 2) * 32;
         const int jl = ((warp & 3) * 32 + lane) ^ kARev;  // output position held by this thread's accumulator row
-        for (int t = 0; t < n_blocks; ++t) {
-            const BlockCoord c = block_coord(a, t, first, stride, n_tiles);
-            const int l = t % nblk;
-            if (l == 0) {  // new tile: row scales (previous tile's epilogue is over: it ended with a barrier)
-                if (tid < kB) {
-                    const int i = c.ib * kB + tid;
-                    const float m = i < a.I ? __ldg(a.rowmax_in + static_cast<size_t>(c.plane) * a.I + i) : 0.0f;
-                    int eb = (__float_as_int(m) >> 23) & 0xff;
-                    eb = min(max(eb, 13), 254);
-                    s_scale[tid] = __int_as_float((266 - eb) << 23);  // max |row| -> [2^12, 2^13)
-                    s_inv[tid] = __int_as_float((eb - 12) << 23);
+        // load cursor (thread 0): the next block to request, two blocks ahead of the one being converted
+        int ld_tile = first, ld_l = 0, ld_u = 0;
+        TileCoord ld_c = tile_coord(a, min(ld_tile, n_tiles - 1));
+        ld_l = ld_c.l0;
+        auto issue_next_load = [&]() {
+            if (ld_tile >= n_tiles) return;
+            mbar_arrive_expect_tx(mbar_tma + (ld_u & 1), kAStage);
+            tma_load_3d(smem + kAOffStage + (ld_u & 1) * kAStage, &tmap, mbar_tma + (ld_u & 1), (ld_c.jb + ld_l - a.nb) * kB, ld_c.ib * kB,
+                        ld_c.plane);
+            ++ld_u;
+            if (++ld_l > ld_c.l1) {
+                ld_tile += stride;
+                if (ld_tile < n_tiles) {
+                    ld_c = tile_coord(a, ld_tile);
+                    ld_l = ld_c.l0;
                 }
-                named_bar_sync(2, kAxThreads);
             }
-            // ---- staging -> registers ----
-            mbar_wait(mbar_tma + (t & 1), (t >> 1) & 1);
-            const float* stage = reinterpret_cast<const float*>(smem + kAOffStage + (t & 1) * kAStage);
-            float4 v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(stage + (q * kAxThreads + tid) * 4);
-            named_bar_sync(2, kAxThreads);  // staging drained
-            if (tid == 0 && t + 2 < n_blocks) issue_load(t + 2);
-            if (t > 0) mbar_wait(mbar_mma, (t - 1) & 1);  // MMAs of block t - 1 complete: X tiles free
-            // ---- registers -> X hi | lo tiles (row = i, K = k) ----
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int f = q * kAxThreads + tid;
-                const int h = f >> 5, w = (f & 31) << 2;
-                const float sc = s_scale[h];
-                __half2 hi[2], lo[2];
-                ax_split2(v[q].x * sc, v[q].y * sc, hi[0], lo[0]);
-                ax_split2(v[q].z * sc, v[q].w * sc, hi[1], lo[1]);
-                const uint32_t off = ax_tile_off(h, w);
-                *reinterpret_cast<uint2*>(smem + kAOffX1 + off) = *reinterpret_cast<uint2*>(hi);
-                *reinterpret_cast<uint2*>(smem + kAOffX2 + off) = *reinterpret_cast<uint2*>(lo);
+        };
+        if (tid == 0) {
+            issue_next_load();
+            issue_next_load();
+        }
+        int u = 0;
+        for (int tile = first; tile < n_tiles; tile += stride) {
+            const TileCoord c = tile_coord(a, tile);
+            // row scales of this tile (the previous tile's epilogue is over: it ended with a barrier)
+            if (tid < kB) {
+                const int i = c.ib * kB + tid;
+                const float m = i < a.I ? __ldg(a.rowmax_in + static_cast<size_t>(c.plane) * a.I + i) : 0.0f;
+                int eb = (__float_as_int(m) >> 23) & 0xff;
+                eb = min(max(eb, 13), 254);
+                s_scale[tid] = __int_as_float((266 - eb) << 23);  // max |row| -> [2^12, 2^13)
+                s_inv[tid] = __int_as_float((eb - 12) << 23);
             }
-            fence_proxy_async();
-            ax_fence_before();
-            named_bar_sync(1, kAxThreads + 32);  // -> MMAs of block t
-            if (l == nblk - 1) {
-                // ---- epilogue of the tile: out[j][i] = (D_main + 2^-11 D_cross) / scale_i ----
-                mbar_wait(mbar_mma, t & 1);
-                ax_fence_after();
-                float dm[32], dc[32];
-                ax_ld32(d_main + lane_base + col_base, dm);
-                ax_ld32(d_cross + lane_base + col_base, dc);
-                ax_ld_wait(dm);
-                ax_ld_wait(dc);
-                const int j = c.jb * kB + jl;
-                const int i0 = c.ib * kB + col_base;
-                float mx = 0.0f;
+            named_bar_sync(2, kAxThreads);
+            for (int l = c.l0; l <= c.l1; ++l, ++u) {
+                // ---- staging -> registers ----
+                mbar_wait(mbar_tma + (u & 1), (u >> 1) & 1);
+                const float* stage = reinterpret_cast<const float*>(smem + kAOffStage + (u & 1) * kAStage);
+                float4 v[8];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    dm[e] = fmaf(dc[e], 1.0f / 2048.0f, dm[e]) * s_inv[col_base + e];
-                    mx = fmaxf(mx, fabsf(dm[e]));
-                }
-                if (j < a.K) {
-                    float* dst = a.out + (static_cast<size_t>(c.plane) * a.K + j) * a.I + i0;
+                for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(stage + (q * kAxThreads + tid) * 4);
+                named_bar_sync(2, kAxThreads);  // staging drained
+                if (tid == 0) issue_next_load();
+                if (u > 0) mbar_wait(mbar_mma, (u - 1) & 1);  // MMAs of the previous block complete: X tiles free
+                // ---- registers -> X hi | lo tiles (row = i, K = k) ----
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        if (i0 + e < a.I) __stcs(reinterpret_cast<float4*>(dst + e), make_float4(dm[e], dm[e + 1], dm[e + 2], dm[e + 3]));
-                    if (a.rowmax_out != nullptr)
-                        atomicMax(reinterpret_cast<int*>(a.rowmax_out + static_cast<size_t>(c.plane) * a.K + j), __float_as_int(mx));
+                for (int q = 0; q < 8; ++q) {
+                    const int f = q * kAxThreads + tid;
+                    const int h = f >> 5, w = (f & 31) << 2;
+                    const float sc = s_scale[h];
+                    __half2 hi[2], lo[2];
+                    ax_split2(v[q].x * sc, v[q].y * sc, hi[0], lo[0]);
+                    ax_split2(v[q].z * sc, v[q].w * sc, hi[1], lo[1]);
+                    const uint32_t off = ax_tile_off(h, w);
+                    *reinterpret_cast<uint2*>(smem + kAOffX1 + off) = *reinterpret_cast<uint2*>(hi);
+                    *reinterpret_cast<uint2*>(smem + kAOffX2 + off) = *reinterpret_cast<uint2*>(lo);
                 }
+                fence_proxy_async();
                 ax_fence_before();
-                named_bar_sync(2, kAxThreads);  // accumulators and scales are free for the next tile
+                named_bar_sync(1, kAxThreads + 32);  // -> MMAs of block u
             }
+            // ---- epilogue of the tile: out[j][i] = (D_main + 2^-11 D_cross) / scale_i ----
+            mbar_wait(mbar_mma, (u - 1) & 1);
+            ax_fence_after();
+            float dm[32], dc[32];
+            ax_ld32(d_main + lane_base + col_base, dm);
+            ax_ld32(d_cross + lane_base + col_base, dc);
+            ax_ld_wait(dm);
+            ax_ld_wait(dc);
+            const int j = c.jb * kB + jl;
+            const int i0 = c.ib * kB + col_base;
+            float mx = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                dm[e] = fmaf(dc[e], 1.0f / 2048.0f, dm[e]) * s_inv[col_base + e];
+                mx = fmaxf(mx, fabsf(dm[e]));
+            }
+            if (j < a.K) {
+                float* dst = a.out + (static_cast<size_t>(c.plane) * a.K + j) * a.I + i0;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    if (i0 + e < a.I) __stcs(reinterpret_cast<float4*>(dst + e), make_float4(dm[e], dm[e + 1], dm[e + 2], dm[e + 3]));
+                if (a.rowmax_out != nullptr)
+                    atomicMax(reinterpret_cast<int*>(a.rowmax_out + static_cast<size_t>(c.plane) * a.K + j), __float_as_int(mx));
+            }
+            ax_fence_before();
+            named_bar_sync(2, kAxThreads);  // accumulators and scales are free for the next tile
         }
     }
     ax_fence_before();
