@@ -30,7 +30,8 @@ namespace {
 constexpr int kB = 128;                        // block edge
 constexpr int kAxThreads = 512;                // compute threads (16 warps)
 constexpr int kAxWarps = kAxThreads / 32;
-constexpr int kAxCta = kAxThreads + 32;        // + the MMA-issuing warp
+constexpr int kAxStoreWarps = 4;               // warps 17..20: epilogue (accumulators -> global), off the critical path
+constexpr int kAxCta = kAxThreads + 32 + 32 * kAxStoreWarps;  // + the MMA-issuing warp + the store warps
 constexpr int kAxMaxNb = 2;                    // radius <= 256
 constexpr uint32_t kALBO = 144, kASBO = 16 * kALBO, kATile = 16 * kASBO;  // padded K-major operand tile (see blur_tc.cu)
 constexpr uint32_t kAStage = kB * kB * 4;      // 65536
@@ -41,7 +42,7 @@ constexpr uint32_t kAStripBytes = 12288;       // (32 * 2 + 31) core matrices x 
 constexpr uint32_t kAOffS1 = kAOffX2 + kATile;
 constexpr uint32_t kAOffS2 = kAOffS1 + kAStripBytes;
 constexpr uint32_t kAOffMisc = kAOffS2 + kAStripBytes;  // s_scale[128], s_inv[128], barriers
-constexpr uint32_t kASmem = kAOffMisc + 1024 + 256;
+constexpr uint32_t kASmem = kAOffMisc + 1536 + 256;
 constexpr uint32_t kAIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // kind::f16, D = f32, M = N = 128, K-major
 constexpr int kARev = 0x78;
 
@@ -138,12 +139,14 @@ __device__ __forceinline__ TileCoord tile_coord(const AxisArgs& a, int tile) {
 __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* s_g = reinterpret_cast<float*>(smem + kAOffX1);  // taps (<= 513), only until the strip is built
-    float* s_scale = reinterpret_cast<float*>(smem + kAOffMisc);  // [128] per input row of the tile
-    float* s_inv = s_scale + kB;                                  // [128]
-    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kAOffMisc + 1024);  // [2]
-    uint64_t* mbar_mma = mbar_tma + 2;  // one phase per block: its MMAs are complete (X tiles free; after the last block: D valid)
-    double* s_red = reinterpret_cast<double*>(mbar_tma + 3);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 4);
+    float* s_scale = reinterpret_cast<float*>(smem + kAOffMisc);  // [128] per input row of the tile being converted
+    float* s_inv = s_scale + kB;                                  // [2][128]: tile parity (read by the store warps one tile later)
+    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kAOffMisc + 1536);  // [2]
+    uint64_t* mbar_mma = mbar_tma + 2;       // one phase per block: its MMAs are complete (X tiles free)
+    uint64_t* mbar_acc_full = mbar_tma + 3;  // [2]: all MMAs of a tile complete, accumulator pair valid
+    uint64_t* mbar_acc_free = mbar_tma + 5;  // [2]: the store warps hold the accumulator pair in registers
+    double* s_red = reinterpret_cast<double*>(mbar_tma + 7);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 8);
     const uint32_t sbase = smem_u32(smem);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,10 +159,14 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
         mbar_init(mbar_tma + 0, 1);
         mbar_init(mbar_tma + 1, 1);
         mbar_init(mbar_mma, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(mbar_acc_full + b, 1);
+            mbar_init(mbar_acc_free + b, kAxStoreWarps);
+        }
         mbar_fence_init();
     }
-    if (warp == kAxWarps) {  // TMEM: D_main = [0, 128), D_cross = [128, 256)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256) : "memory");
+    if (warp == kAxWarps) {  // TMEM: tile parity b: D_main = [256 b, 256 b + 128), D_cross = [256 b + 128, 256 b + 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (a.rule == BGAN_RULE_EXPLICIT) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -182,18 +189,21 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
     __syncthreads();
     ax_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t d_main = tmem, d_cross = tmem + 128;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
+    const int jl = ((warp & 3) * 32 + lane) ^ kARev;  // output position held by this thread's accumulator row
     asm volatile("griddepcontrol.wait;" ::: "memory");  // `in` may be written, `out` may still be read by the previous grid
 
     // Blocks are numbered u = 0, 1, ... in the order (tile, l); block u uses staging[u & 1] and phase u of mbar_mma.
     if (warp == kAxWarps) {
         // ================= MMA issuer =================================================================
-        int u = 0;
-        for (int tile = first; tile < n_tiles; tile += stride) {
+        int u = 0, n = 0;
+        for (int tile = first; tile < n_tiles; tile += stride, ++n) {
             const TileCoord c = tile_coord(a, tile);
+            const uint32_t d_main = tmem + (n & 1) * 256, d_cross = d_main + 128;
             for (int l = c.l0; l <= c.l1; ++l, ++u) {
                 named_bar_sync(1, kAxThreads + 32);  // X tiles of block u written
                 if (lane == 0) {
+                    if (l == c.l0 && n >= 2) mbar_wait(mbar_acc_free + (n & 1), ((n - 2) >> 1) & 1);  // accumulator pair drained
                     ax_fence_after();
                     const uint64_t a1 = ax_desc(sbase + kAOffS1 + l * 16 * 128, 128, 128), a2 = ax_desc(sbase + kAOffS2 + l * 16 * 128, 128, 128);
                     const uint64_t b1 = ax_desc(sbase + kAOffX1, kALBO, kASBO), b2 = ax_desc(sbase + kAOffX2, kALBO, kASBO);
@@ -205,15 +215,52 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
 #pragma unroll
                     for (int k = 0; k < 8; ++k) ax_mma(d_main, a1 + k * 16, b1 + k * 18, acc0 | (k > 0));
                     ax_commit(mbar_mma);
+                    if (l == c.l1) ax_commit(mbar_acc_full + (n & 1));
                 }
                 __syncwarp();
             }
         }
+    } else if (warp > kAxWarps) {
+        // ================= store warps: out[j][i] = (D_main + 2^-11 D_cross) / scale_i =========================
+        int n = 0;
+        for (int tile = first; tile < n_tiles; tile += stride, ++n) {
+            const TileCoord c = tile_coord(a, tile);
+            const uint32_t d_main = tmem + (n & 1) * 256, d_cross = d_main + 128;
+            const float* inv = s_inv + (n & 1) * kB;
+            mbar_wait(mbar_acc_full + (n & 1), (n >> 1) & 1);
+            ax_fence_after();
+            const int j = c.jb * kB + jl;
+            float* dst = a.out + (static_cast<size_t>(c.plane) * a.K + j) * a.I + c.ib * kB;
+            float mx = 0.0f;
+#pragma unroll 1
+            for (int cg = 0; cg < 4; ++cg) {
+                float dm[32], dc[32];
+                ax_ld32(d_main + lane_base + cg * 32, dm);
+                ax_ld32(d_cross + lane_base + cg * 32, dc);
+                ax_ld_wait(dm);
+                ax_ld_wait(dc);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    dm[e] = fmaf(dc[e], 1.0f / 2048.0f, dm[e]) * inv[cg * 32 + e];
+                    mx = fmaxf(mx, fabsf(dm[e]));
+                }
+                if (cg == 3) {  // accumulators and scales of this tile have been read: the tile after next may reuse them
+                    ax_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(mbar_acc_free + (n & 1));
+                }
+                if (j < a.K) {
+                    const int i0 = c.ib * kB + cg * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        if (i0 + e < a.I) __stcs(reinterpret_cast<float4*>(dst + cg * 32 + e), make_float4(dm[e], dm[e + 1], dm[e + 2], dm[e + 3]));
+                }
+            }
+            if (j < a.K && a.rowmax_out != nullptr)
+                atomicMax(reinterpret_cast<int*>(a.rowmax_out + static_cast<size_t>(c.plane) * a.K + j), __float_as_int(mx));
+        }
     } else {
         // ================= compute warps ==============================================================
-        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-        const int col_base = (warp >> 2) * 32;
-        const int jl = ((warp & 3) * 32 + lane) ^ kARev;  // output position held by this thread's accumulator row
         // load cursor (thread 0): the next block to request, two blocks ahead of the one being converted
         int ld_tile = first, ld_l = 0, ld_u = 0;
         TileCoord ld_c = tile_coord(a, min(ld_tile, n_tiles - 1));
@@ -236,17 +283,19 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
             issue_next_load();
             issue_next_load();
         }
-        int u = 0;
-        for (int tile = first; tile < n_tiles; tile += stride) {
+        int u = 0, n = 0;
+        for (int tile = first; tile < n_tiles; tile += stride, ++n) {
             const TileCoord c = tile_coord(a, tile);
-            // row scales of this tile (the previous tile's epilogue is over: it ended with a barrier)
+            // row scales of this tile.  s_scale is only read by the compute warps (the barrier at the end of the previous
+            // block ordered those reads); s_inv[n & 1] was last read by the store warps for tile n - 2.
+            if (n >= 2) mbar_wait(mbar_acc_free + (n & 1), ((n - 2) >> 1) & 1);
             if (tid < kB) {
                 const int i = c.ib * kB + tid;
                 const float m = i < a.I ? __ldg(a.rowmax_in + static_cast<size_t>(c.plane) * a.I + i) : 0.0f;
                 int eb = (__float_as_int(m) >> 23) & 0xff;
                 eb = min(max(eb, 13), 254);
                 s_scale[tid] = __int_as_float((266 - eb) << 23);  // max |row| -> [2^12, 2^13)
-                s_inv[tid] = __int_as_float((eb - 12) << 23);
+                s_inv[(n & 1) * kB + tid] = __int_as_float((eb - 12) << 23);
             }
             named_bar_sync(2, kAxThreads);
             for (int l = c.l0; l <= c.l1; ++l, ++u) {
@@ -276,37 +325,11 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
                 ax_fence_before();
                 named_bar_sync(1, kAxThreads + 32);  // -> MMAs of block u
             }
-            // ---- epilogue of the tile: out[j][i] = (D_main + 2^-11 D_cross) / scale_i ----
-            mbar_wait(mbar_mma, (u - 1) & 1);
-            ax_fence_after();
-            float dm[32], dc[32];
-            ax_ld32(d_main + lane_base + col_base, dm);
-            ax_ld32(d_cross + lane_base + col_base, dc);
-            ax_ld_wait(dm);
-            ax_ld_wait(dc);
-            const int j = c.jb * kB + jl;
-            const int i0 = c.ib * kB + col_base;
-            float mx = 0.0f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                dm[e] = fmaf(dc[e], 1.0f / 2048.0f, dm[e]) * s_inv[col_base + e];
-                mx = fmaxf(mx, fabsf(dm[e]));
-            }
-            if (j < a.K) {
-                float* dst = a.out + (static_cast<size_t>(c.plane) * a.K + j) * a.I + i0;
-#pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    if (i0 + e < a.I) __stcs(reinterpret_cast<float4*>(dst + e), make_float4(dm[e], dm[e + 1], dm[e + 2], dm[e + 3]));
-                if (a.rowmax_out != nullptr)
-                    atomicMax(reinterpret_cast<int*>(a.rowmax_out + static_cast<size_t>(c.plane) * a.K + j), __float_as_int(mx));
-            }
-            ax_fence_before();
-            named_bar_sync(2, kAxThreads);  // accumulators and scales are free for the next tile
         }
     }
     ax_fence_before();
     __syncthreads();
-    if (warp == kAxWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    if (warp == kAxWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
