@@ -34,6 +34,7 @@ bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, c
 int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream);
 
 // blur_axis.cu: two-pass tensor-core path for large planes and wide blurs
+bool blur_axis_shape_ok(int planes, int H, int W, int ES, int radius);
 bool blur_axis_eligible(int planes, int H, int W, int ES, int radius, const float* x, const float* y);
 size_t blur_axis_workspace_bytes(int planes, int H, int W);
 int blur_axis_launch(const float* x, float* y, int planes, int H, int W, int rule, float std_eff, int radius, const float* taps_dev, void* ws,
@@ -546,9 +547,7 @@ extern "C" int bgan_blur_taps_f32(int rule, float std_eff, int radius, float* ta
 extern "C" size_t bgan_blur2d_workspace_bytes(int n, int c, int height, int width, int layout, int radius) {
     Geometry g;
     if (!geometry(n, c, height, width, layout, &g) || radius < 0) return 0;
-    // (pointer alignment is not known here: 16-byte aligned dummies stand for "aligned like a fresh allocation")
-    const float* aligned = reinterpret_cast<const float*>(uintptr_t(256));
-    if (blur_axis_eligible(g.planes, g.H, g.Wc, g.ES, radius, aligned, aligned)) return blur_axis_workspace_bytes(g.planes, g.H, g.Wc);
+    if (blur_axis_shape_ok(g.planes, g.H, g.Wc, g.ES, radius)) return blur_axis_workspace_bytes(g.planes, g.H, g.Wc);
     Plan fused = choose_plan(g.H, g.Wc, g.ES, radius, radius);
     if (fused.ok) return 0;
     return static_cast<size_t>(g.planes) * g.H * g.Wc * sizeof(float);

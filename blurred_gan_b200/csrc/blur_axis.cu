@@ -400,14 +400,19 @@ int launch_axis(const float* in, float* out, const float* rowmax_in, float* rowm
 
 }  // namespace
 
-// planes of H x W floats, contiguous (NCHW, or NHWC with one channel)
-bool blur_axis_eligible(int planes, int H, int W, int ES, int radius, const float* x, const float* y) {
+// planes of H x W floats, contiguous (NCHW, or NHWC with one channel).  Shape part of the eligibility: also decides the
+// workspace size, so it must not depend on the device or on pointer values.
+bool blur_axis_shape_ok(int planes, int H, int W, int ES, int radius) {
     const char* off = getenv("BGAN_BLUR_NO_AXIS_TC");
     if (off && atoi(off)) return false;
     const char* min_r = getenv("BGAN_BLUR_AXIS_MIN_R");
     const int rmin = min_r ? atoi(min_r) : 12;
-    return ES == 1 && planes > 0 && H >= 256 && W >= 256 && H % 4 == 0 && W % 4 == 0 && radius >= rmin && radius <= kAxMaxNb * kB &&
-           reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 && axis_encode_fn() != nullptr;
+    return ES == 1 && planes > 0 && H >= 256 && W >= 256 && H % 4 == 0 && W % 4 == 0 && radius >= rmin && radius <= kAxMaxNb * kB;
+}
+
+bool blur_axis_eligible(int planes, int H, int W, int ES, int radius, const float* x, const float* y) {
+    return blur_axis_shape_ok(planes, H, W, ES, radius) && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+           reinterpret_cast<uintptr_t>(y) % 16 == 0 && axis_encode_fn() != nullptr;
 }
 
 // scratch: the transposed intermediate plus the two row-maximum arrays
