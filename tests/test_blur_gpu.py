@@ -393,3 +393,46 @@ def test_direct_path_explicit_asymmetric_taps():
     yh = ops.blur2d_taps(_dev(xh_np), torch.from_numpy(asym).cuda(), ops.LAYOUT_NHWC)
     assert ops.last_blur_path() == 5
     assert_close(yh, bo.blur_nhwc(xh_np, asym), "direct path NHWC, asymmetric taps")
+
+
+def test_randomised_kernel_selection_and_parity():
+    """Seeded random shapes, layouts, radii and (asymmetric) explicit taps across every kernel of the dispatch table:
+    whichever kernel runs, the result is the oracle's zero-padded correlation along W then H."""
+    from blurred_gan_b200 import ops
+
+    rs = np.random.RandomState(2024)
+    seen = set()
+    cases = []
+    for _ in range(6):   # 128 x 128: direct (r <= 5 / 4) or tensor-core kernel
+        cases.append(("NCHW", (int(rs.randint(1, 6)), int(rs.randint(1, 4)), 128, 128), int(rs.randint(1, 90))))
+        cases.append(("NHWC", (int(rs.randint(1, 6)), 128, 128, 3), int(rs.randint(1, 70))))
+    for _ in range(5):   # large planes: two-pass tensor-core kernel (r >= 12), tile kernel otherwise
+        h, w = 4 * int(rs.randint(64, 140)), 4 * int(rs.randint(64, 140))
+        cases.append(("NCHW", (1, int(rs.randint(1, 3)), h, w), int(rs.randint(2, 200))))
+    for _ in range(5):   # everything else: tile kernel
+        cases.append(("NCHW", (2, 2, int(rs.randint(5, 120)), int(rs.randint(5, 200))), int(rs.randint(1, 40))))
+    for layout, shape, radius in cases:
+        taps = rs.rand(2 * radius + 1).astype(np.float32)
+        taps /= taps.sum()
+        x = (rs.rand(*shape) * 2 - 1).astype(np.float32) * np.float32(10.0 ** rs.randint(-3, 4))
+        lay = ops.LAYOUT_NCHW if layout == "NCHW" else ops.LAYOUT_NHWC
+        got = ops.blur2d_taps(_dev(x), _dev(taps), lay)
+        seen.add(ops.last_blur_path())
+        want = bo.blur_nchw(x, taps) if layout == "NCHW" else bo.blur_nhwc(x, taps)
+        for n in range(shape[0]):
+            assert_close(got[n], want[n], "%s %s radius %d path %d" % (layout, shape, radius, ops.last_blur_path()))
+    # the tensor-core kernel of 128 x 128 planes generates its taps in-kernel (tap rules only): random sigmas, both rules
+    from blurred_gan_b200.gaussian_blur import blur_images
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    for _ in range(6):
+        std = float(rs.uniform(1.2, 30.0))
+        x = (rs.rand(int(rs.randint(1, 5)), 3, 128, 128) * 2 - 1).astype(np.float32) * np.float32(10.0 ** rs.randint(-3, 4))
+        got = GaussianBlur(std).cuda()(_dev(x))
+        seen.add(ops.last_blur_path())
+        assert_close(got, bo.gaussian_blur_torch_ref(x, std), "torch rule std=%g" % std)
+        xh = np.ascontiguousarray(x.transpose(0, 2, 3, 1))
+        got = blur_images(_dev(xh), std)
+        seen.add(ops.last_blur_path())
+        assert_close(got, bo.blur_images_tf_ref(xh, std), "tf rule NHWC std=%g" % std)
+    assert {4, 5, 6} <= seen and (seen & {1, 2, 3}), seen
