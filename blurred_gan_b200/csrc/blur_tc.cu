@@ -57,6 +57,8 @@ constexpr uint32_t kOffO1 = kOffT2 + kTileBytes;  // X1, later Z1
 constexpr uint32_t kOffO2 = kOffO1 + kTileBytes;  // X2, later Z2
 constexpr uint32_t kOffMisc = kOffO2 + kTileBytes;
 constexpr uint32_t kSmemTc = kOffMisc + 1024 /* taps */ + 256;
+constexpr int kDefaultVariant = 3;
+constexpr int kDefaultPrefetch = 1;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 // instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -70,6 +72,7 @@ struct TcArgs {
     int rule;
     float std_eff;
     int radius;
+    int pf;  // L2 prefetch distance in planes (per CTA)
 };
 
 __device__ __forceinline__ uint32_t tile_off(int row, int k) {
@@ -164,6 +167,28 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32])
         : "r"(taddr));
 }
 
+// 16 consecutive fp32 columns / 8 consecutive 32-bit columns (the split stage works in halves to keep registers free
+// for the next plane, which is already on its way from staging to the fp16 tiles)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait16(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]),
+                   "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // a -> (fp16(a), fp16((a - fp16(a)) * 2^11)) for two values at a time
 __device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
     hi = __floats2half2_rn(a, b);
@@ -199,6 +224,25 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t z_tmem, 
     for (int k = 1; k < 8; ++k) umma_f16_ts(d_tmem, a1 + 8 * k, db1 + k * kStep, 1);
 }
 
+// The same GEMM2 in three pieces, so that the cross terms of K = h in [0, 64) can start while the second half of D1 is
+// still being split: cross(half 0), cross(half 1), then the main term on the accumulator pre-scaled by 2^-11.
+__device__ __forceinline__ void issue_gemm_ts_cross(uint32_t d_tmem, uint32_t z_tmem, uint32_t b1, uint32_t b2, int half) {
+    const uint64_t db1 = smem_desc(b1), db2 = smem_desc(b2);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+    const uint32_t a1 = z_tmem, a2 = z_tmem + 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16_ts(d_tmem, a1 + 8 * (4 * half + k), db2 + (4 * half + k) * kStep, (half | k) != 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16_ts(d_tmem, a2 + 8 * (4 * half + k), db1 + (4 * half + k) * kStep, 1);
+}
+__device__ __forceinline__ void issue_gemm_ts_main(uint32_t d_tmem, uint32_t z_tmem, uint32_t b1) {
+    const uint64_t db1 = smem_desc(b1);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+    umma_f16_ts_scale_d11(d_tmem, z_tmem, db1);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) umma_f16_ts(d_tmem, z_tmem + 8 * k, db1 + k * kStep, 1);
+}
+
 // NHWC (es == 3): TMA cannot walk the innermost dimension with an element stride (elementStrides[0] is ignored for
 // non-interleaved maps) and the channel stride of 12 bytes is not a legal tensor-map stride either, so the compute
 // threads gather channel c of image n with 4-byte cp.async (LDGSTS) straight into the same row-major [128][128] staging
@@ -229,7 +273,13 @@ __device__ __forceinline__ void gather_plane_load(unsigned char* stage, const fl
 //
 // The tensor pipe only idles during split; the global store, the staging read and the fp16 conversion of the
 // next plane all hide behind the MMAs, and the TMA load of plane p+2 has a whole iteration to land.
+//
+// kV selects the schedule (bit 0: the staging read of plane p+1 runs in the shadow of GEMM1(p) and its fp16 conversion in the
+// shadow of GEMM2(p), instead of both behind GEMM2(p); bit 1: D1 is split in two K-halves and GEMM2's cross terms of the first
+// half are issued while the second half is still being split).
+template <int kV>
 __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+    constexpr bool kEarlyFetch = (kV & 1) != 0, kHalfSplit = (kV & 2) != 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
     float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
@@ -247,6 +297,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     int n_stamp = 0;
     auto stamp = [&]() {
         if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 120) a.trace[1 + n_stamp++] = clock64();
+    };
+    // second and third timeline (debug): lane 0 of the MMA warp -> trace[128 ..], lane 0 of the first store warp -> trace[256 ..]
+    auto stamp_role = [&](int base) {
+        if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && n_stamp < 120) {
+            a.trace[base + 1 + n_stamp++] = clock64();
+            a.trace[base] = n_stamp;
+        }
     };
     if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) a.trace[126] = static_cast<long long>(global_timer_ns());
     stamp();  // 0: kernel start
@@ -268,6 +325,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             asm volatile("griddepcontrol.wait;" ::: "memory");
             mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
             tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, static_cast<int>(blockIdx.x));
+            // the L2 prefetch runs a.pf planes ahead of the loads: start it for planes 1 .. pf (the first fetch issues the
+            // load of plane 1 and the prefetch of plane 1 + pf)
+            for (int j = 1; j <= a.pf; ++j) {
+                const int pp = static_cast<int>(blockIdx.x + j * gridDim.x);
+                if (pp < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, pp);
+            }
         }
     }
     __syncwarp();
@@ -338,18 +401,42 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             named_bar_sync(1, kTcThreads + 32);  // X(p) tiles written
             if (lane == 0) {
                 tc_fence_after();
+                stamp_role(128);  // G1 issue starts
                 issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, sbase + kOffO1, sbase + kOffO2);  // D1 = T X^T
                 umma_commit(mbar_g1);
+                stamp_role(128);  // G1 issued
             }
             __syncwarp();
-            named_bar_sync(1, kTcThreads + 32);  // Z(p) written to TMEM
-            if (lane == 0) {
-                if (it >= 2) mbar_wait(mbar_d2free + (it & 1), ((it - 2) >> 1) & 1);  // D2[it & 1] drained by the store warps
-                tc_fence_after();
-                issue_gemm_ts(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
-                umma_commit(mbar_g2 + (it & 1));
+            if constexpr (!kHalfSplit) {
+                named_bar_sync(1, kTcThreads + 32);  // Z(p) written to TMEM
+                if (lane == 0) {
+                    if (it >= 2) mbar_wait(mbar_d2free + (it & 1), ((it - 2) >> 1) & 1);  // D2[it & 1] drained by the store warps
+                    tc_fence_after();
+                    stamp_role(128);  // G2 issue starts
+                    issue_gemm_ts(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
+                    umma_commit(mbar_g2 + (it & 1));
+                    stamp_role(128);  // G2 issued
+                }
+                __syncwarp();
+            } else {
+                named_bar_sync(3, kTcThreads + 32);  // Z(p), K = h in [0, 64), written to TMEM
+                if (lane == 0) {
+                    if (it >= 2) mbar_wait(mbar_d2free + (it & 1), ((it - 2) >> 1) & 1);
+                    tc_fence_after();
+                    stamp_role(128);  // G2 (first half) issue starts
+                    issue_gemm_ts_cross(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2, 0);
+                }
+                __syncwarp();
+                named_bar_sync(4, kTcThreads + 32);  // Z(p), K in [64, 128)
+                if (lane == 0) {
+                    tc_fence_after();
+                    issue_gemm_ts_cross(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2, 1);
+                    issue_gemm_ts_main(d2 + (it & 1) * 128, zp, sbase + kOffT1);
+                    umma_commit(mbar_g2 + (it & 1));
+                    stamp_role(128);  // G2 issued
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= kStoreWarp0) {
         // ================= store warps: D2 = Y^T -> global, coalesced along w' =================================
@@ -357,6 +444,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         for (int p = first; p + stride < a.planes; p += stride, ++it) {  // (the last plane is drained by the compute warps)
             mbar_wait(mbar_g2 + (it & 1), (it >> 1) & 1);
             tc_fence_after();
+            if (warp == kStoreWarp0) stamp_role(256);  // G2(p) complete, store starts
             const float inv = s_inv[it & 3];
             float* yp = a.y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
             const size_t ld = static_cast<size_t>(kP) * a.es;  // floats between consecutive output rows h'
@@ -373,6 +461,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
 #pragma unroll
                 for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(c * 32 + j) * ld, o[j] * inv);
             }
+            if (warp == kStoreWarp0) stamp_role(256);  // last store of plane p issued
         }
     } else {
         // ================= compute warps ==============================================================
@@ -383,7 +472,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         // staging -> registers + per-warp max into s_max[buf]; ends with a barrier of the compute warps, after which
         // staging is free and thread 0 starts the TMA load of the plane after next
         auto fetch = [&](int buf, int next_plane) {
+            stamp();  // fetch: waiting for the plane
             mbar_wait(mbar_tma, par_tma);
+            stamp();  // fetch: plane landed
             par_tma ^= 1;
             float m = 0.0f;
 #pragma unroll
@@ -400,7 +491,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             } else if (tid == 0 && next_plane < a.planes) {
                 mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
                 tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, next_plane);
-                if (next_plane + stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, next_plane + stride);  // warm L2 one more ahead
+                // warm L2 further ahead (a.pf planes beyond the one being loaded)
+                if (a.pf > 0 && next_plane + a.pf * stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, next_plane + a.pf * stride);
             }
         };
         // registers -> X1, X2 tiles (B operand of GEMM1: row = h, K = w), scaled so that max|x| is in [2^12, 2^13)
@@ -436,13 +528,18 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             tc_fence_before();
             named_bar_sync(1, kTcThreads + 32);  // -> GEMM1(p)
             stamp();                             // +0
+            if constexpr (kEarlyFetch) {
+                // while GEMM1(p) runs: the next plane goes from staging into registers (its load was issued an iteration ago)
+                if (has_next) fetch((it + 1) & 1, p + 2 * stride);
+            }
+            stamp();                             // +1: (early fetch) next plane in registers
             mbar_wait(mbar_g1, it & 1);          // GEMM1(p) complete: D1 valid, X tiles free
             if (it > 0) mbar_wait(mbar_g2 + ((it - 1) & 1), ((it - 1) >> 1) & 1);  // GEMM2(p - 1) complete: Z free
             tc_fence_after();
             stamp();                             // +2
 
             // ---- split: D1 (fp32) -> Z^T hi | lo as packed fp16 back into TMEM (A operand of GEMM2: lane = w', K = h)
-            {
+            if constexpr (!kEarlyFetch && !kHalfSplit) {
                 float z[32];
                 tmem_ld32_nowait(d1 + lane_base + col_base, z);
                 tmem_ld_wait(z);
@@ -457,16 +554,47 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
                 tmem_st16(zp + lane_base + (col_base >> 1), zh);
                 tmem_st16(zp + 64 + lane_base + (col_base >> 1), zl);
                 tmem_st_wait();
+                tc_fence_before();
+                named_bar_sync(1, kTcThreads + 32);  // -> GEMM2(p)
+            } else {
+                // 16 columns at a time (the registers of the next plane stay live across this stage).  With kHalfSplit a
+                // warp owns columns [16 g, 16 g + 16) and [64 + 16 g, 64 + 16 g + 16), g = warp / 4: after the first pass
+                // K = h in [0, 64) of Z is complete and the MMA warp starts GEMM2's cross terms on it.
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int c0 = kHalfSplit ? 64 * half + (col_base >> 1) : col_base + 16 * half;
+                    float z[16];
+                    tmem_ld16_nowait(d1 + lane_base + c0, z);
+                    tmem_ld_wait16(z);
+                    uint32_t zh[8], zl[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        __half2 hi, lo;
+                        split2(z[2 * e], z[2 * e + 1], hi, lo);
+                        zh[e] = *reinterpret_cast<uint32_t*>(&hi);
+                        zl[e] = *reinterpret_cast<uint32_t*>(&lo);
+                    }
+                    tmem_st8(zp + lane_base + (c0 >> 1), zh);
+                    tmem_st8(zp + 64 + lane_base + (c0 >> 1), zl);
+                    if constexpr (kHalfSplit) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        named_bar_arrive(3 + half, kTcThreads + 32);  // -> GEMM2(p), this K-half
+                    }
+                }
+                if constexpr (!kHalfSplit) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    named_bar_sync(1, kTcThreads + 32);  // -> GEMM2(p)
+                }
             }
-            tc_fence_before();
-            named_bar_sync(1, kTcThreads + 32);  // -> GEMM2(p)
             stamp();                             // +3: split done
+            // while GEMM2(p) runs: (staging -> registers ->) fp16 tiles of the next plane (free since GEMM1(p) completed)
             if (has_next) {
-                fetch((it + 1) & 1, p + 2 * stride);
-                stamp();                         // +4: next plane in registers
+                if constexpr (!kEarlyFetch) fetch((it + 1) & 1, p + 2 * stride);
                 convert((it + 1) & 1, it + 1);
             }
-            stamp();                             // +5: next plane converted
+            stamp();                             // +4: next plane converted
         }
         // ---- drain: all 16 compute warps store the last plane (one 32-column group each) ---------------------
         {
@@ -550,12 +678,16 @@ int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float
     int dev = 0;
     BGAN_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
         attr_dev = dev;
     }
     const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
     const int units = planes * es;  // 128 x 128 channel planes
-    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, x, y, es, units, rule, std_eff, radius};
+    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, x, y, es, units, rule, std_eff, radius, kDefaultPrefetch};
+    if (const char* v = getenv("BGAN_TC_PF")) a.pf = std::max(0, atoi(v));  // experiments only
     // balanced persistent grid: every CTA runs the same number of rounds (768 planes on 148 SMs -> 128 CTAs x 6 planes
     // rather than 28 CTAs x 6 + 120 x 5), so that the HBM-bound steady state has no latency-bound tail round
     const int sms = device_sm_count();
@@ -577,7 +709,14 @@ int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float
     const char* no_pdl = getenv("BGAN_BLUR_NO_PDL");
     cfg.attrs = attr;
     cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
-    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel, a, tmap));
+    int variant = kDefaultVariant;
+    if (const char* v = getenv("BGAN_TC_VARIANT")) variant = atoi(v) & 3;  // experiments only
+    switch (variant) {
+        case 0: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<0>, a, tmap)); break;
+        case 1: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<1>, a, tmap)); break;
+        case 2: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<2>, a, tmap)); break;
+        default: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<3>, a, tmap)); break;
+    }
     return 0;
 }
 

@@ -1,39 +1,54 @@
-"""Print the clock64 phase stamps of CTA 0 of the tensor-core blur kernel (debug aid)."""
+"""Print the clock64 phase stamps of CTA 0 of the tensor-core blur kernel (debug aid).
+
+Three timelines: compute thread 0, lane 0 of the MMA warp, lane 0 of the first store warp.
+    BGAN_TC_VARIANT=3 BGAN_TC_PF=2 python tools/trace_tc.py [std]
+"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from blurred_gan_b200 import _lib
 lib = _lib.load()
 n, c, h, w = 256, 3, 128, 128
-x = torch.rand(n, c, h, w, device="cuda") * 2 - 1
-y = torch.empty_like(x)
-trace = torch.zeros(128, dtype=torch.int64, device="cuda")
-k, r, se = _lib.blur_plan(0, 5.0, h, w)
+std = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
+variant = int(os.environ.get("BGAN_TC_VARIANT", "3"))
+early = bool(variant & 1)
+xs = [torch.rand(n, c, h, w, device="cuda") * 2 - 1 for _ in range(4)]
+ys = [torch.empty_like(x) for x in xs]
+trace = torch.zeros(512, dtype=torch.int64, device="cuda")
+k, r, se = _lib.blur_plan(0, std, h, w)
 sp = torch.cuda.current_stream().cuda_stream
-for rep in range(3):
-    if rep == 2:
+for rep in range(4):
+    if rep == 3:
         os.environ["BGAN_TC_TRACE_PTR"] = str(trace.data_ptr())
-    _lib.check(lib.bgan_blur2d_f32(x.data_ptr(), y.data_ptr(), n, c, h, w, 0, 0, se, r, None, None, 0, sp), "blur")
-    torch.cuda.synchronize()
+    _lib.check(lib.bgan_blur2d_f32(xs[rep].data_ptr(), ys[rep].data_ptr(), n, c, h, w, 0, 0, se, r, None, None, 0, sp), "blur")
+torch.cuda.synchronize()
 t = trace.cpu().tolist()
 cnt = t[0]
 st = t[1:1 + cnt]
-print("stamps", cnt)
 base = st[0]
-names = ["start", "init+alloc", "taps", "chunk-table", "T-copied", "prologue", "first-convert"]
-per = ["barX", "G1done", "split+barZ", "fetch-next", "convert-next"]
-i = 0
+print("variant %d pf %s: %d stamps; %.0f cycles in %.0f ns -> %.3f GHz" % (
+    variant, os.environ.get("BGAN_TC_PF", "default"), cnt, t[125] - st[0], t[127] - t[126], (t[125] - st[0]) / max(t[127] - t[126], 1)))
+labels = ["start", "init+alloc", "taps", "chunk-table", "T-copied", "prologue", "fetch0-wait", "fetch0-landed", "first-convert"]
+iters = 6
+for it in range(iters):
+    has_next = it + 1 < iters
+    labels.append("it%d bar->G1" % it)
+    if early and has_next:
+        labels += ["it%d   fetch-wait" % it, "it%d   fetch-landed" % it]
+    labels += ["it%d fetched(early)" % it, "it%d G1done" % it, "it%d split" % it]
+    if not early and has_next:
+        labels += ["it%d   fetch-wait" % it, "it%d   fetch-landed" % it]
+    labels.append("it%d converted" % it)
+labels.append("drain")
 prev = base
-print("clock: %.0f cycles in %.0f ns -> %.3f GHz" % (t[125] - st[0], t[127] - t[126], (t[125] - st[0]) / max(t[127] - t[126], 1)))
-for k in range(7):
-    print("%-12s %8d  (+%d)" % (names[k], st[k] - base, st[k] - prev)); prev = st[k]
-i = 7
-it = 0
-NP = len(per)
-while cnt - i >= NP + 1:
-    print("-- iteration", it)
-    for k in range(NP):
-        print("  %-10s %8d  (+%d)" % (per[k], st[i + k] - base, st[i + k] - prev)); prev = st[i + k]
-    i += NP; it += 1
-for k in range(i, cnt):
-    print("%-12s %8d  (+%d)" % ("drain", st[k] - base, st[k] - prev)); prev = st[k]
+for i, v in enumerate(st):
+    print("%-22s %8d  (+%d)" % (labels[i] if i < len(labels) else "?", v - base, v - prev))
+    prev = v
+for name, b, per in (("MMA warp", 128, ["G1 issue", "G1 issued", "G2 issue", "G2 issued"]), ("store warp", 256, ["store start", "store issued"])):
+    c2 = t[b]
+    s2 = t[b + 1:b + 1 + c2]
+    print("--", name)
+    prev = base
+    for i, v in enumerate(s2):
+        print("  it%d %-14s %8d  (+%d)" % (i // len(per), per[i % len(per)], v - base, v - prev))
+        prev = v
