@@ -40,8 +40,8 @@ constexpr int kTcThreads = 512;                          // compute threads; one
 constexpr int kTcWarps = kTcThreads / 32;                // 16: TMEM lane quadrant = warp & 3, column group = warp >> 2
 constexpr int kMmaWarp = kTcWarps;                       // warp 16 issues the MMAs
 constexpr int kStoreWarp0 = kTcWarps + 1;                // warps 17..20 drain D2 to global memory
-constexpr int kStoreWarps = 4;
-constexpr int kCtaThreads = kTcThreads + 32 + 32 * kStoreWarps;  // 672
+constexpr int kStoreWarps = 8;                           // (schedules without bit 2 use the first four)
+constexpr int kCtaThreads = kTcThreads + 32 + 32 * kStoreWarps;  // 800
 constexpr int kColsPerWarp = kP / (kTcWarps / 4);        // 32 accumulator columns per thread in the epilogues
 constexpr int kF4PerThread = kP * kP / 4 / kTcThreads;   // 8 float4 of the plane per thread
 // operand tile: K-major, no swizzle, core matrix = 8 rows x 16 bytes.  Core matrices adjacent in K are
@@ -57,11 +57,13 @@ constexpr uint32_t kOffO1 = kOffT2 + kTileBytes;  // X1, later Z1
 constexpr uint32_t kOffO2 = kOffO1 + kTileBytes;  // X2, later Z2
 constexpr uint32_t kOffMisc = kOffO2 + kTileBytes;
 constexpr uint32_t kSmemTc = kOffMisc + 1024 /* taps */ + 256;
-constexpr int kDefaultVariant = 3;
+constexpr int kDefaultVariant = 7;
 constexpr int kDefaultPrefetch = 1;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 // instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+constexpr uint32_t kIdescN64 = (1u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct TcArgs {
     long long* trace;  // debug: clock64 stamps of CTA 0 / thread 0 (nullptr in production)
@@ -72,7 +74,8 @@ struct TcArgs {
     int rule;
     float std_eff;
     int radius;
-    int pf;  // L2 prefetch distance in planes (per CTA)
+    int pf;   // L2 prefetch distance in planes (per CTA)
+    int dbg;  // experiments only: switch stages off (results are wrong then)
 };
 
 __device__ __forceinline__ uint32_t tile_off(int row, int k) {
@@ -196,6 +199,20 @@ __device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& l
     lo = __floats2half2_rn((a - back.x) * kLoScale, (b - back.y) * kLoScale);
 }
 
+// data-side split without the 2^11 scaling of the remainder (see "raw lo" below)
+__device__ __forceinline__ void split2_raw(float a, float b, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hi);
+    lo = __floats2half2_rn(a - back.x, b - back.y);
+}
+template <bool kRaw>
+__device__ __forceinline__ void split2_sel(float a, float b, __half2& hi, __half2& lo) {
+    if constexpr (kRaw)
+        split2_raw(a, b, hi, lo);
+    else
+        split2(a, b, hi, lo);
+}
+
 // the three products of one GEMM into one accumulator: cross terms, then the main term on the
 // accumulator pre-scaled by 2^-11.  Each product is 8 instructions of K = 16.
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a1, uint32_t a2, uint32_t b1, uint32_t b2) {
@@ -224,6 +241,42 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t z_tmem, 
     for (int k = 1; k < 8; ++k) umma_f16_ts(d_tmem, a1 + 8 * k, db1 + k * kStep, 1);
 }
 
+// GEMM1 for one half of the plane's rows (N = 64 columns of D1): the two halves complete separately, so that the first
+// half of D1 is split while the tensor pipe works on the second
+__device__ __forceinline__ void umma_f16_ts_n64(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate, bool scale_d11) {
+    if (scale_d11) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p, 11;\n\t"
+            "}\n" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(bdesc), "r"(kIdescN64), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+            "}\n" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(bdesc), "r"(kIdescN64), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void issue_gemm_ts_n64(uint32_t d_tmem, uint32_t t_tmem, uint32_t b1, uint32_t b2) {
+    const uint64_t db1 = smem_desc(b1), db2 = smem_desc(b2);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+    const uint32_t a1 = t_tmem, a2 = t_tmem + 64;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_f16_ts_n64(d_tmem, a1 + 8 * k, db2 + k * kStep, k > 0, false);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) umma_f16_ts_n64(d_tmem, a2 + 8 * k, db1 + k * kStep, 1, false);
+    umma_f16_ts_n64(d_tmem, a1, db1, 1, true);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) umma_f16_ts_n64(d_tmem, a1 + 8 * k, db1 + k * kStep, 1, false);
+}
+
 // The same GEMM2 in three pieces, so that the cross terms of K = h in [0, 64) can start while the second half of D1 is
 // still being split: cross(half 0), cross(half 1), then the main term on the accumulator pre-scaled by 2^-11.
 __device__ __forceinline__ void issue_gemm_ts_cross(uint32_t d_tmem, uint32_t z_tmem, uint32_t b1, uint32_t b2, int half) {
@@ -241,6 +294,66 @@ __device__ __forceinline__ void issue_gemm_ts_main(uint32_t d_tmem, uint32_t z_t
     umma_f16_ts_scale_d11(d_tmem, z_tmem, db1);
 #pragma unroll
     for (int k = 1; k < 8; ++k) umma_f16_ts(d_tmem, z_tmem + 8 * k, db1 + k * kStep, 1);
+}
+
+// ---- "raw lo" operand convention (schedule bit 4) -----------------------------------------------------------------------
+// The data-side operands (X, Z) keep their fp16 remainder unscaled: after the per-plane power-of-two scaling max|x| is in
+// [2^12, 2^13), so a remainder only becomes an fp16 subnormal for elements below 2^-15 of the plane maximum, where the
+// absolute error (<= 2^-25) is irrelevant.  That saves one FMUL per element in both conversion stages.  T keeps its
+// remainder scaled by 2^11 (taps are small).  Order of the products into one accumulator:
+//   T_lo' x DATA_hi   (scale 2^11)   ->  accumulator * 2^-11 + T_hi x DATA_hi   ->  + T_hi x DATA_lo
+template <bool kN64>
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t accumulate, bool scale_d11) {
+    constexpr uint32_t idesc = kN64 ? kIdescN64 : kIdesc;
+    if (scale_d11) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p, 11;\n\t"
+            "}\n" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+            "}\n" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    }
+}
+// GEMM1 (A = T hi | lo' in TMEM, B = X hi / raw lo tiles), whole plane or one N = 64 half
+template <bool kN64>
+__device__ __forceinline__ void issue_g1_rawlo(uint32_t d_tmem, uint32_t t_tmem, uint32_t x_hi, uint32_t x_lo) {
+    const uint64_t dh = smem_desc(x_hi), dl = smem_desc(x_lo);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mma_ts<kN64>(d_tmem, t_tmem + 64 + 8 * k, dh + k * kStep, k > 0, false);
+    mma_ts<kN64>(d_tmem, t_tmem, dh, 1, true);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mma_ts<kN64>(d_tmem, t_tmem + 8 * k, dh + k * kStep, 1, false);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mma_ts<kN64>(d_tmem, t_tmem + 8 * k, dl + k * kStep, 1, false);
+}
+// GEMM2 (A = Z hi | raw lo in TMEM, B = T hi / lo' tiles): Z_hi x T_lo' for K-steps [k0, k1), then everything else
+__device__ __forceinline__ void issue_g2_rawlo_cross(uint32_t d_tmem, uint32_t z_tmem, uint32_t t_lo, int k0, int k1) {
+    const uint64_t dl = smem_desc(t_lo);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k >= k0 && k < k1) mma_ts<false>(d_tmem, z_tmem + 8 * k, dl + k * kStep, k > 0, false);
+}
+__device__ __forceinline__ void issue_g2_rawlo_main(uint32_t d_tmem, uint32_t z_tmem, uint32_t t_hi) {
+    const uint64_t dh = smem_desc(t_hi);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+    mma_ts<false>(d_tmem, z_tmem, dh, 1, true);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mma_ts<false>(d_tmem, z_tmem + 8 * k, dh + k * kStep, 1, false);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mma_ts<false>(d_tmem, z_tmem + 64 + 8 * k, dh + k * kStep, 1, false);
 }
 
 // NHWC (es == 3): TMA cannot walk the innermost dimension with an element stride (elementStrides[0] is ignored for
@@ -280,6 +393,16 @@ __device__ __forceinline__ void gather_plane_load(unsigned char* stage, const fl
 template <int kV>
 __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr bool kEarlyFetch = (kV & 1) != 0, kHalfSplit = (kV & 2) != 0;
+    // bit 2: T also lives in TMEM as the A operand of GEMM1 (TS mode: GEMM1 only reads X from shared memory, half the
+    // operand traffic); D2 is then single-buffered and eight store warps pull it into registers as soon as GEMM2 completes
+    constexpr bool kTsG1 = (kV & 4) != 0;
+    // bit 3 (needs bits 1 and 2): GEMM1 runs as two N = 64 halves (rows h < 64, h >= 64) that complete separately
+    constexpr bool kSplitG1 = (kV & 8) != 0;
+    static_assert(!kSplitG1 || (kTsG1 && kHalfSplit), "kSplitG1 needs kTsG1 and kHalfSplit");
+    constexpr bool kRawLo = (kV & 16) != 0;  // bit 4 (needs bit 2): see "raw lo" above
+    static_assert(!kRawLo || kTsG1, "kRawLo needs kTsG1");
+    constexpr int kActiveStoreWarps = kTsG1 ? 8 : 4;
+    constexpr int kStoreCols = kP / (kActiveStoreWarps / 4);  // D2 columns (= output rows h') per store warp: 128 or 64
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
     float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
@@ -287,7 +410,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     uint64_t* mbar_g1 = mbar_tma + 1;
     uint64_t* mbar_g2 = mbar_tma + 2;      // [2]: GEMM2 into D2[b] complete
     uint64_t* mbar_d2free = mbar_tma + 4;  // [2]: D2[b] has been read out
-    double* s_red = reinterpret_cast<double*>(mbar_tma + 6);
+    uint64_t* mbar_g1b = mbar_tma + 6;  // kSplitG1: second half of GEMM1 complete
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 7);
     float* s_inv = reinterpret_cast<float*>(mbar_tma + 8);   // [4] ring: 1 / scale of plane it
     float* s_max = s_inv + 4;                                // [2][16]
@@ -315,10 +438,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         tma_prefetch_desc(&tmap);
         mbar_init(mbar_tma, a.es == 1 ? 1 : kTcThreads);  // TMA transaction bytes / one cp.async arrival per compute thread
         mbar_init(mbar_g1, 1);
+        mbar_init(mbar_g1b, 1);
         mbar_init(mbar_g2 + 0, 1);
         mbar_init(mbar_g2 + 1, 1);
-        mbar_init(mbar_d2free + 0, kStoreWarps);
-        mbar_init(mbar_d2free + 1, kStoreWarps);
+        mbar_init(mbar_d2free + 0, kActiveStoreWarps);
+        mbar_init(mbar_d2free + 1, kActiveStoreWarps);
         mbar_fence_init();
         // the first plane starts moving before anything else is set up (but not before the producer of x is done)
         if (a.es == 1) {
@@ -334,7 +458,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         }
     }
     __syncwarp();
-    if (warp == 0) {  // TMEM columns: D1 = [0, 128), Z^T as fp16 hi | lo = [128, 256), D2 double-buffered = [256, 384) / [384, 512)
+    // TMEM columns: D1 = [0, 128), Z^T as fp16 hi | lo = [128, 256), D2 double-buffered = [256, 384) / [384, 512)
+    // kTsG1:        T as fp16 hi | lo = [0, 128), D1 = [128, 256), Z^T = [256, 384), D2 = [384, 512)
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -373,6 +499,25 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     }
     __syncthreads();
     stamp();  // chunk table
+    if constexpr (kTsG1) {
+        if (warp < kTcWarps) {  // T hi | lo -> TMEM: lane = row w', 32-bit column = two consecutive K (= w) elements
+            tc_fence_after();
+            const uint32_t t_tmem = *s_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + (warp >> 2) * 16;
+            const int trow = (warp & 3) * 32 + lane;
+            uint32_t th[16], tl[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = ((warp >> 2) * 4 + c) * 8 - trow + a.radius + 7;
+                const bool band = i >= 0 && i < n_taps + 7;
+                const uint4 h4 = band ? s_chi[i] : make_uint4(0, 0, 0, 0), l4 = band ? s_clo[i] : make_uint4(0, 0, 0, 0);
+                th[4 * c] = h4.x, th[4 * c + 1] = h4.y, th[4 * c + 2] = h4.z, th[4 * c + 3] = h4.w;
+                tl[4 * c] = l4.x, tl[4 * c + 1] = l4.y, tl[4 * c + 2] = l4.z, tl[4 * c + 3] = l4.w;
+            }
+            tmem_st16(t_tmem, th);
+            tmem_st16(t_tmem + 64, tl);
+            tmem_st_wait();
+        }
+    }
     for (int idx = tid; idx < kP * 16; idx += kCtaThreads) {
         const int row = idx & 127, chunk = idx >> 7;  // lanes <-> consecutive rows: conflict-free 16-byte loads and stores
         const int i = chunk * 8 - row + a.radius + 7;
@@ -387,10 +532,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t d1 = tmem, zp = tmem + 128, d2 = tmem + 256;
+    const uint32_t tT = tmem, d1 = tmem + (kTsG1 ? 128 : 0), zp = d1 + 128, d2 = zp + 128;
+    (void)tT;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;  // TMEM lane quadrant of this warp
     const int row = (warp & 3) * 32 + lane;  // accumulator row (= w') owned by this thread
     const int first = blockIdx.x, stride = gridDim.x;
+    // D2 buffer of iteration `it`, and the parity of the mbarrier phase that its `it`-th use completes
+    auto d2_buf = [](int it) { return kTsG1 ? 0 : (it & 1); };
+    auto d2_par = [](int it) { return kTsG1 ? (it & 1) : ((it >> 1) & 1); };
+    constexpr int kD2Depth = kTsG1 ? 1 : 2;
     stamp();  // 1: prologue (TMEM, taps, T tiles) done
     asm volatile("griddepcontrol.wait;" ::: "memory");  // (all threads: y may still be read by the previous grid)
 
@@ -402,37 +552,68 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             if (lane == 0) {
                 tc_fence_after();
                 stamp_role(128);  // G1 issue starts
-                issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, sbase + kOffO1, sbase + kOffO2);  // D1 = T X^T
-                umma_commit(mbar_g1);
+                if constexpr (kSplitG1) {
+                    if constexpr (kRawLo) {
+                        issue_g1_rawlo<true>(d1, tT, sbase + kOffO1, sbase + kOffO2);
+                        umma_commit(mbar_g1);
+                        issue_g1_rawlo<true>(d1 + 64, tT, sbase + kOffO1 + 8 * kSBO, sbase + kOffO2 + 8 * kSBO);
+                    } else {
+                        issue_gemm_ts_n64(d1, tT, sbase + kOffO1, sbase + kOffO2);
+                        umma_commit(mbar_g1);
+                        issue_gemm_ts_n64(d1 + 64, tT, sbase + kOffO1 + 8 * kSBO, sbase + kOffO2 + 8 * kSBO);
+                    }
+                    umma_commit(mbar_g1b);
+                } else {
+                    if constexpr (kRawLo)
+                        issue_g1_rawlo<false>(d1, tT, sbase + kOffO1, sbase + kOffO2);
+                    else if constexpr (kTsG1)
+                        issue_gemm_ts(d1, tT, sbase + kOffO1, sbase + kOffO2);
+                    else
+                        issue_gemm(d1, sbase + kOffT1, sbase + kOffT2, sbase + kOffO1, sbase + kOffO2);  // D1 = T X^T
+                    umma_commit(mbar_g1);
+                }
                 stamp_role(128);  // G1 issued
             }
             __syncwarp();
             if constexpr (!kHalfSplit) {
                 named_bar_sync(1, kTcThreads + 32);  // Z(p) written to TMEM
                 if (lane == 0) {
-                    if (it >= 2) mbar_wait(mbar_d2free + (it & 1), ((it - 2) >> 1) & 1);  // D2[it & 1] drained by the store warps
+                    if (it >= kD2Depth) mbar_wait(mbar_d2free + d2_buf(it), d2_par(it - kD2Depth));  // D2 drained by the store warps
                     tc_fence_after();
                     stamp_role(128);  // G2 issue starts
-                    issue_gemm_ts(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
-                    umma_commit(mbar_g2 + (it & 1));
+                    if constexpr (kRawLo) {
+                        issue_g2_rawlo_cross(d2, zp, sbase + kOffT2, 0, 8);
+                        issue_g2_rawlo_main(d2, zp, sbase + kOffT1);
+                    } else {
+                        issue_gemm_ts(d2 + d2_buf(it) * 128, zp, sbase + kOffT1, sbase + kOffT2);  // D2 = Z^T T = Y^T
+                    }
+                    umma_commit(mbar_g2 + d2_buf(it));
                     stamp_role(128);  // G2 issued
                 }
                 __syncwarp();
             } else {
                 named_bar_sync(3, kTcThreads + 32);  // Z(p), K = h in [0, 64), written to TMEM
                 if (lane == 0) {
-                    if (it >= 2) mbar_wait(mbar_d2free + (it & 1), ((it - 2) >> 1) & 1);
+                    if (it >= kD2Depth) mbar_wait(mbar_d2free + d2_buf(it), d2_par(it - kD2Depth));
                     tc_fence_after();
                     stamp_role(128);  // G2 (first half) issue starts
-                    issue_gemm_ts_cross(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2, 0);
+                    if constexpr (kRawLo)
+                        issue_g2_rawlo_cross(d2, zp, sbase + kOffT2, 0, 4);
+                    else
+                        issue_gemm_ts_cross(d2 + d2_buf(it) * 128, zp, sbase + kOffT1, sbase + kOffT2, 0);
                 }
                 __syncwarp();
                 named_bar_sync(4, kTcThreads + 32);  // Z(p), K in [64, 128)
                 if (lane == 0) {
                     tc_fence_after();
-                    issue_gemm_ts_cross(d2 + (it & 1) * 128, zp, sbase + kOffT1, sbase + kOffT2, 1);
-                    issue_gemm_ts_main(d2 + (it & 1) * 128, zp, sbase + kOffT1);
-                    umma_commit(mbar_g2 + (it & 1));
+                    if constexpr (kRawLo) {
+                        issue_g2_rawlo_cross(d2, zp, sbase + kOffT2, 4, 8);
+                        issue_g2_rawlo_main(d2, zp, sbase + kOffT1);
+                    } else {
+                        issue_gemm_ts_cross(d2 + d2_buf(it) * 128, zp, sbase + kOffT1, sbase + kOffT2, 1);
+                        issue_gemm_ts_main(d2 + d2_buf(it) * 128, zp, sbase + kOffT1);
+                    }
+                    umma_commit(mbar_g2 + d2_buf(it));
                     stamp_role(128);  // G2 issued
                 }
                 __syncwarp();
@@ -440,28 +621,56 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         }
     } else if (warp >= kStoreWarp0) {
         // ================= store warps: D2 = Y^T -> global, coalesced along w' =================================
-        int it = 0;
-        for (int p = first; p + stride < a.planes; p += stride, ++it) {  // (the last plane is drained by the compute warps)
-            mbar_wait(mbar_g2 + (it & 1), (it >> 1) & 1);
-            tc_fence_after();
-            if (warp == kStoreWarp0) stamp_role(256);  // G2(p) complete, store starts
-            const float inv = s_inv[it & 3];
-            float* yp = a.y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
-            const size_t ld = static_cast<size_t>(kP) * a.es;  // floats between consecutive output rows h'
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float o[32];
-                tmem_ld32_nowait(d2 + (it & 1) * 128 + lane_base + c * 32, o);
-                tmem_ld_wait(o);
-                if (c == 3) {  // everything of D2[it & 1] is in registers: hand the buffer back
+        if (warp < kStoreWarp0 + kActiveStoreWarps) {
+            const int c0 = ((warp - kStoreWarp0) >> 2) * kStoreCols;  // first D2 column (= output row h') of this warp
+            int it = 0;
+            // (without kTsG1 the last plane is drained by the compute warps)
+            for (int p = first; p + (kTsG1 ? 0 : stride) < a.planes; p += stride, ++it) {
+                mbar_wait(mbar_g2 + d2_buf(it), d2_par(it));
+                tc_fence_after();
+                if (warp == kStoreWarp0) stamp_role(256);  // G2(p) complete, store starts
+                const float inv = s_inv[it & 3];
+                float* yp = a.y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
+                const size_t ld = static_cast<size_t>(kP) * a.es;  // floats between consecutive output rows h'
+                if constexpr (kTsG1) {
+                    // the whole 64-column share goes to registers first, so that D2 is free again after ~1000 cycles
+                    float o0[32], o1[32];
+                    tmem_ld32_nowait(d2 + lane_base + c0, o0);
+                    tmem_ld32_nowait(d2 + lane_base + c0 + 32, o1);
+                    tmem_ld_wait(o0);
+                    tmem_ld_wait(o1);
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(mbar_d2free + (it & 1));
-                }
+                    if (lane == 0) mbar_arrive(mbar_d2free);
+                    float* q = yp + static_cast<size_t>(c0) * ld;
+                    // (the empty asm keeps the compiler from materialising all 64 addresses up front, which spills)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(c * 32 + j) * ld, o[j] * inv);
+                    for (int j = 0; j < 32; ++j, q += ld) {
+                        asm volatile("" : "+l"(q));
+                        __stcs(q, o0[j] * inv);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j, q += ld) {
+                        asm volatile("" : "+l"(q));
+                        __stcs(q, o1[j] * inv);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        float o[32];
+                        tmem_ld32_nowait(d2 + d2_buf(it) * 128 + lane_base + c * 32, o);
+                        tmem_ld_wait(o);
+                        if (c == 3) {  // everything of D2[it & 1] is in registers: hand the buffer back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(mbar_d2free + d2_buf(it));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) __stcs(yp + static_cast<size_t>(c * 32 + j) * ld, o[j] * inv);
+                    }
+                }
+                if (warp == kStoreWarp0) stamp_role(256);  // last store of plane p issued
             }
-            if (warp == kStoreWarp0) stamp_role(256);  // last store of plane p issued
         }
     } else {
         // ================= compute warps ==============================================================
@@ -509,8 +718,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
                 const int f = j * kTcThreads + tid;  // float4 index: row h = f / 32, w = 4 * (f % 32)
                 const int h = f >> 5, w = (f & 31) << 2;
                 __half2 hi[2], lo[2];
-                split2(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
-                split2(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
+                split2_sel<kRawLo>(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
+                split2_sel<kRawLo>(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
                 const uint32_t off = tile_off(h, w);
                 *reinterpret_cast<uint2*>(smem + kOffO1 + off) = *reinterpret_cast<uint2*>(hi);
                 *reinterpret_cast<uint2*>(smem + kOffO2 + off) = *reinterpret_cast<uint2*>(lo);
@@ -534,7 +743,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             }
             stamp();                             // +1: (early fetch) next plane in registers
             mbar_wait(mbar_g1, it & 1);          // GEMM1(p) complete: D1 valid, X tiles free
-            if (it > 0) mbar_wait(mbar_g2 + ((it - 1) & 1), ((it - 1) >> 1) & 1);  // GEMM2(p - 1) complete: Z free
+            if (it > 0) mbar_wait(mbar_g2 + d2_buf(it - 1), d2_par(it - 1));  // GEMM2(p - 1) complete: Z free
             tc_fence_after();
             stamp();                             // +2
 
@@ -563,6 +772,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     const int c0 = kHalfSplit ? 64 * half + (col_base >> 1) : col_base + 16 * half;
+                    if constexpr (kSplitG1) {
+                        if (half == 1) {
+                            mbar_wait(mbar_g1b, it & 1);  // second half of D1 valid, X tiles free
+                            tc_fence_after();
+                        }
+                    }
                     float z[16];
                     tmem_ld16_nowait(d1 + lane_base + c0, z);
                     tmem_ld_wait16(z);
@@ -570,7 +785,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         __half2 hi, lo;
-                        split2(z[2 * e], z[2 * e + 1], hi, lo);
+                        split2_sel<kRawLo>(z[2 * e], z[2 * e + 1], hi, lo);
                         zh[e] = *reinterpret_cast<uint32_t*>(&hi);
                         zl[e] = *reinterpret_cast<uint32_t*>(&lo);
                     }
@@ -597,7 +812,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             stamp();                             // +4: next plane converted
         }
         // ---- drain: all 16 compute warps store the last plane (one 32-column group each) ---------------------
-        {
+        if constexpr (!kTsG1) {
             const int last = it - 1, p_last = first + last * stride;
             mbar_wait(mbar_g2 + (last & 1), (last >> 1) & 1);
             tc_fence_after();
@@ -621,6 +836,373 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
+
+// =====================================================================================================================
+// Two planes in flight.  T sits in TMEM (A operand of GEMM1), the accumulator of GEMM1 is double-buffered and split to
+// fp16 *in place* (a thread's 32 fp32 columns become its 16 hi + 16 lo packed columns, so no thread ever writes a column
+// that another one still has to read), D2 is single-buffered and pulled into registers by eight store warps:
+//
+//   TMEM columns   T hi | lo' [0, 128)    D1 / Z of even planes [128, 256)    D1 / Z of odd planes [256, 384)    D2 [384, 512)
+//
+//   tensor pipe     G1(i+1)                                  G2(i)                              G1(i+2) ...
+//   compute warps   split(i) | staging -> registers (i+2)    | convert(i+2) -> X tiles (free: G1(i+1) done)
+//   store warps     ... D2(i-1) -> global ...                                  D2(i) -> registers -> global
+//
+// The tensor pipe never waits for the split (it works on the next plane's GEMM1 meanwhile) and the compute warps never
+// hold the next plane in registers across the split.  Operands use the "raw lo" convention above.
+__device__ __forceinline__ void issue_g2_inplace(uint32_t d_tmem, uint32_t dz, uint32_t t_hi, uint32_t t_lo) {
+    const uint64_t dh = smem_desc(t_hi), dl = smem_desc(t_lo);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;
+    // K-step k (h in [16 k, 16 k + 16)): Z_hi at column 32 (k / 2) + 8 (k % 2), Z_lo 16 columns further
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mma_ts<false>(d_tmem, dz + 32 * (k >> 1) + 8 * (k & 1), dl + k * kStep, k > 0, false);
+    mma_ts<false>(d_tmem, dz, dh, 1, true);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mma_ts<false>(d_tmem, dz + 32 * (k >> 1) + 8 * (k & 1), dh + k * kStep, 1, false);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mma_ts<false>(d_tmem, dz + 32 * (k >> 1) + 8 * (k & 1) + 16, dh + k * kStep, 1, false);
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_pipe_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
+    float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
+    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kOffMisc + 1024);
+    uint64_t* mbar_g1 = mbar_tma + 1;      // [2]: GEMM1 of an even / odd plane complete
+    uint64_t* mbar_g2 = mbar_tma + 3;      // GEMM2 complete (D2 valid)
+    uint64_t* mbar_d2free = mbar_tma + 4;  // D2 is in the store warps' registers
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_tma + 7);
+    float* s_inv = reinterpret_cast<float*>(mbar_tma + 8);  // [4] ring: 1 / scale of plane it
+    float* s_max = s_inv + 4;                               // [2][16]
+    const uint32_t sbase = smem_u32(smem);
+    constexpr int kBarA0 = 1, kBarA1 = 3, kBarB0 = 4;  // named barriers: X(i) ready (even / odd i), Z(i) ready (4 + i % 2); 2 = fetch
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n_stamp = 0;
+    auto stamp = [&]() {
+        if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 120) a.trace[1 + n_stamp++] = clock64();
+    };
+    auto stamp_role = [&](int base) {
+        if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && n_stamp < 120) {
+            a.trace[base + 1 + n_stamp++] = clock64();
+            a.trace[base] = n_stamp;
+        }
+    };
+    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) a.trace[126] = static_cast<long long>(global_timer_ns());
+    stamp();  // kernel start
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(mbar_tma, a.es == 1 ? 1 : kTcThreads);
+        mbar_init(mbar_g1 + 0, 1);
+        mbar_init(mbar_g1 + 1, 1);
+        mbar_init(mbar_g2, 1);
+        mbar_init(mbar_d2free, kStoreWarps);
+        mbar_fence_init();
+        if (a.es == 1) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+            tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, static_cast<int>(blockIdx.x));
+            for (int j = 1; j <= a.pf; ++j) {
+                const int pp = static_cast<int>(blockIdx.x + j * gridDim.x);
+                if (pp < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, pp);
+            }
+        }
+    }
+    __syncwarp();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    stamp();  // barrier init / TMEM alloc
+    const int n_taps = 2 * a.radius + 1;
+    if (warp == 1) {
+        float part = 0.0f;
+        for (int t = lane; t < n_taps; t += 32) {
+            const float g = raw_tap(a.rule, a.std_eff, t - a.radius);
+            s_g[t] = g;
+            part += g;
+        }
+        const float tot = static_cast<float>(warp_sum(static_cast<double>(part)));
+        __syncwarp();
+        for (int t = lane; t < n_taps; t += 32) s_g[t] = s_g[t] / tot;
+    }
+    __syncthreads();
+    if (a.es != 1 && warp < kTcWarps) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        gather_plane_load(smem + kOffStage, a.x, mbar_tma, static_cast<int>(blockIdx.x), a.es, tid);
+    }
+    stamp();  // taps
+    uint4* s_chi = reinterpret_cast<uint4*>(smem + kOffO1);
+    uint4* s_clo = s_chi + 272;
+    for (int j = tid; j < (n_taps + 7) * 4; j += kCtaThreads) {
+        const int i = j >> 2, e = j & 3;
+        const int da = i - 7 + 2 * e, db = da + 1;
+        __half2 hi, lo;
+        split2((da >= 0 && da < n_taps) ? s_g[da] : 0.0f, (db >= 0 && db < n_taps) ? s_g[db] : 0.0f, hi, lo);
+        reinterpret_cast<__half2*>(s_chi + i)[e] = hi;
+        reinterpret_cast<__half2*>(s_clo + i)[e] = lo;
+    }
+    __syncthreads();
+    stamp();  // chunk table
+    if (warp < kTcWarps) {  // T hi | lo' -> TMEM: lane = row w', 32-bit column = two consecutive K (= w) elements
+        tc_fence_after();
+        const uint32_t t_tmem = *s_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + (warp >> 2) * 16;
+        const int trow = (warp & 3) * 32 + lane;
+        uint32_t th[16], tl[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = ((warp >> 2) * 4 + c) * 8 - trow + a.radius + 7;
+            const bool band = i >= 0 && i < n_taps + 7;
+            const uint4 h4 = band ? s_chi[i] : make_uint4(0, 0, 0, 0), l4 = band ? s_clo[i] : make_uint4(0, 0, 0, 0);
+            th[4 * c] = h4.x, th[4 * c + 1] = h4.y, th[4 * c + 2] = h4.z, th[4 * c + 3] = h4.w;
+            tl[4 * c] = l4.x, tl[4 * c + 1] = l4.y, tl[4 * c + 2] = l4.z, tl[4 * c + 3] = l4.w;
+        }
+        tmem_st16(t_tmem, th);
+        tmem_st16(t_tmem + 64, tl);
+        tmem_st_wait();
+    }
+    for (int idx = tid; idx < kP * 16; idx += kCtaThreads) {
+        const int row = idx & 127, chunk = idx >> 7;
+        const int i = chunk * 8 - row + a.radius + 7;
+        const bool band = i >= 0 && i < n_taps + 7;
+        const uint32_t off = tile_off(row, chunk * 8);
+        *reinterpret_cast<uint4*>(smem + kOffT1 + off) = band ? s_chi[i] : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(smem + kOffT2 + off) = band ? s_clo[i] : make_uint4(0, 0, 0, 0);
+    }
+    stamp();  // T in TMEM and in shared memory
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t tT = tmem, dz = tmem + 128, d2 = tmem + 384;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int row = (warp & 3) * 32 + lane;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int n = first < a.planes ? (a.planes - first + stride - 1) / stride : 0;  // planes of this CTA
+    stamp();  // prologue done
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == kMmaWarp) {
+        // ================= MMA issuer: G1(0), then G1(i + 1), G2(i) ===================================================
+        if (n > 0) {
+            named_bar_sync(kBarA0, kTcThreads + 32);
+            if (lane == 0) {
+                tc_fence_after();
+                stamp_role(128);
+                issue_g1_rawlo<false>(dz, tT, sbase + kOffO1, sbase + kOffO2);
+                umma_commit(mbar_g1);
+                stamp_role(128);
+            }
+            __syncwarp();
+        }
+        for (int i = 0; i < n; ++i) {
+            if (i + 1 < n) {
+                named_bar_sync(((i + 1) & 1) ? kBarA1 : kBarA0, kTcThreads + 32);  // X(i + 1) tiles written
+                if (lane == 0) {
+                    tc_fence_after();
+                    stamp_role(128);  // G1 issue starts
+                    issue_g1_rawlo<false>(dz + ((i + 1) & 1) * 128, tT, sbase + kOffO1, sbase + kOffO2);
+                    umma_commit(mbar_g1 + ((i + 1) & 1));
+                    stamp_role(128);  // G1 issued
+                }
+                __syncwarp();
+            }
+            named_bar_sync(kBarB0 + (i & 1), kTcThreads + 32);  // Z(i) written (in place)
+            if (lane == 0) {
+                if (i >= 1) mbar_wait(mbar_d2free, (i - 1) & 1);  // D2(i - 1) is in the store warps' registers
+                tc_fence_after();
+                stamp_role(128);  // G2 issue starts
+                issue_g2_inplace(d2, dz + (i & 1) * 128, sbase + kOffT1, sbase + kOffT2);
+                umma_commit(mbar_g2);
+                stamp_role(128);  // G2 issued
+            }
+            __syncwarp();
+        }
+    } else if (warp >= kStoreWarp0) {
+        // ================= store warps: D2 = Y^T -> registers -> global, coalesced along w' ===========================
+        const int c0 = ((warp - kStoreWarp0) >> 2) * 64;  // first D2 column (= output row h') of this warp
+        for (int i = 0; i < n; ++i) {
+            const int p = first + i * stride;
+            mbar_wait(mbar_g2, i & 1);
+            tc_fence_after();
+            if (warp == kStoreWarp0) stamp_role(256);  // G2(i) complete
+            const float inv = s_inv[i & 3];
+            float* q = a.y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
+            const size_t ld = static_cast<size_t>(kP) * a.es;  // floats between consecutive output rows h'
+            q += static_cast<size_t>(c0) * ld;
+            float o0[32], o1[32];
+            if (!(a.dbg & 2)) {
+                tmem_ld32_nowait(d2 + lane_base + c0, o0);
+                tmem_ld32_nowait(d2 + lane_base + c0 + 32, o1);
+                tmem_ld_wait(o0);
+                tmem_ld_wait(o1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o0[j] = o1[j] = inv;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mbar_d2free);
+            // (the empty asm keeps the compiler from materialising all 64 addresses up front, which spills)
+            if (!(a.dbg & 1)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j, q += ld) {
+                    asm volatile("" : "+l"(q));
+                    __stcs(q, o0[j] * inv);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j, q += ld) {
+                    asm volatile("" : "+l"(q));
+                    __stcs(q, o1[j] * inv);
+                }
+            } else if (o0[3] + o1[5] == 12345.678f) {
+                __stcs(q, o0[0]);
+            }
+            if (warp == kStoreWarp0) stamp_role(256);  // stores of plane i issued
+        }
+    } else {
+        // ================= compute warps ==============================================================================
+        const int col_base = (warp >> 2) * kColsPerWarp;
+        uint32_t par_tma = 0;
+        float4 v[kF4PerThread];
+        bool buf_first = true;  // (debug flag 32: only the first plane is really loaded)
+        auto fetch = [&](int buf, int next_plane) {
+            stamp();  // fetch: waiting for the plane
+            const bool reload = !(a.dbg & 32) || buf_first;
+            if (reload) {
+                mbar_wait(mbar_tma, par_tma);
+                par_tma ^= 1;
+            }
+            stamp();  // fetch: plane landed
+            float m = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kF4PerThread; ++j) {
+                if (!(a.dbg & 8))
+                    v[j] = *reinterpret_cast<const float4*>(stage + (j * kTcThreads + tid) * 4);
+                else
+                    v[j] = make_float4(1.0f, 0.5f, 0.25f, 0.125f);
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) s_max[buf * kTcWarps + warp] = m;
+            named_bar_sync(2, kTcThreads);
+            buf_first = false;
+            if (a.dbg & 32) {
+            } else if (a.es != 1) {
+                if (next_plane < a.planes) gather_plane_load(smem + kOffStage, a.x, mbar_tma, next_plane, a.es, tid);
+            } else if (tid == 0 && next_plane < a.planes) {
+                mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
+                tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, next_plane);
+                if (a.pf > 0 && next_plane + a.pf * stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, next_plane + a.pf * stride);
+            }
+        };
+        auto convert = [&](int buf, int it_of_plane) {
+            float m = s_max[buf * kTcWarps];
+#pragma unroll
+            for (int w = 1; w < kTcWarps; ++w) m = fmaxf(m, s_max[buf * kTcWarps + w]);
+            int eb = (__float_as_int(m) >> 23) & 0xff;
+            eb = min(max(eb, 13), 254);
+            const float scale = __int_as_float((266 - eb) << 23);
+            if (tid == 0) s_inv[it_of_plane & 3] = __int_as_float((eb - 12) << 23);
+#pragma unroll
+            for (int j = 0; j < kF4PerThread; ++j) {
+                const int f = j * kTcThreads + tid;
+                const int h = f >> 5, w = (f & 31) << 2;
+                __half2 hi[2], lo[2];
+                split2_raw(v[j].x * scale, v[j].y * scale, hi[0], lo[0]);
+                split2_raw(v[j].z * scale, v[j].w * scale, hi[1], lo[1]);
+                const uint32_t off = tile_off(h, w);
+                if (!(a.dbg & 16) || it_of_plane == 0) {
+                    *reinterpret_cast<uint2*>(smem + kOffO1 + off) = *reinterpret_cast<uint2*>(hi);
+                    *reinterpret_cast<uint2*>(smem + kOffO2 + off) = *reinterpret_cast<uint2*>(lo);
+                }
+            }
+            fence_proxy_async();
+        };
+
+        int g1_waited = -1;  // GEMM1 of planes <= g1_waited is known to be complete
+        auto wait_g1 = [&](int i) {
+            if (g1_waited < i) {
+                mbar_wait(mbar_g1 + (i & 1), (i >> 1) & 1);
+                g1_waited = i;
+            }
+            tc_fence_after();
+        };
+        if (n > 0) {
+            fetch(0, first + stride);
+            convert(0, 0);
+            named_bar_arrive(kBarA0, kTcThreads + 32);  // -> G1(0)
+            stamp();  // first plane converted
+            if (n > 1) {
+                fetch(1, first + 2 * stride);
+                wait_g1(0);  // X tiles free
+                convert(1, 1);
+                named_bar_arrive(kBarA1, kTcThreads + 32);  // -> G1(1)
+            }
+            stamp();  // second plane converted
+        }
+        for (int i = 0; i < n; ++i) {
+            wait_g1(i);
+            stamp();  // +0: D1(i) valid
+            // ---- split(i), in place: this thread's fp32 columns [32 g, 32 g + 32) -> hi [32 g, +16) | lo [32 g + 16, +16) -----
+            {
+                const uint32_t base = dz + (i & 1) * 128 + lane_base + col_base;
+                float z[32];
+                if (!(a.dbg & 4)) {
+                    tmem_ld32_nowait(base, z);
+                    tmem_ld_wait(z);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) z[e] = static_cast<float>(e + i);
+                }
+                uint32_t zh[16], zl[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    __half2 hi, lo;
+                    split2_raw(z[2 * e], z[2 * e + 1], hi, lo);
+                    zh[e] = *reinterpret_cast<uint32_t*>(&hi);
+                    zl[e] = *reinterpret_cast<uint32_t*>(&lo);
+                }
+                if (!(a.dbg & 4)) {
+                    tmem_st16(base, zh);
+                    tmem_st16(base + 16, zl);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                named_bar_arrive(kBarB0 + (i & 1), kTcThreads + 32);  // -> G2(i)
+            }
+            stamp();  // +1: split done
+            if (i + 2 < n) {
+                fetch(i & 1, first + (i + 3) * stride);  // plane i + 2: staging -> registers; starts the load of plane i + 3
+                wait_g1(i + 1);                          // X tiles free
+                stamp();                                 // +4: G1(i + 1) complete
+                convert(i & 1, i + 2);
+                named_bar_arrive(((i + 2) & 1) ? kBarA1 : kBarA0, kTcThreads + 32);  // -> G1(i + 2)
+            }
+            stamp();  // +5: plane i + 2 converted
+        }
+    }
+    if (a.trace != nullptr && blockIdx.x == 0 && tid == 0) {
+        a.trace[0] = n_stamp;
+        a.trace[127] = static_cast<long long>(global_timer_ns());
+        a.trace[125] = clock64();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+using TcKernel = void (*)(const TcArgs, const CUtensorMap);
+constexpr int kNumVariants = 13;
+constexpr TcKernel kVariants[kNumVariants] = {blur_tc128_kernel<0>, blur_tc128_kernel<1>, blur_tc128_kernel<2>, blur_tc128_kernel<3>,
+                                              blur_tc128_kernel<4>, blur_tc128_kernel<5>, blur_tc128_kernel<6>, blur_tc128_kernel<7>,
+                                              blur_tc128_kernel<14>, blur_tc128_kernel<15>,   // [8], [9]: with bit 3
+                                              blur_tc128_kernel<23>, blur_tc128_kernel<31>,   // [10], [11]: 7 / 15 with bit 4
+                                              blur_tc128_pipe_kernel};                        // [12]: two planes in flight
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -678,15 +1260,14 @@ int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float
     int dev = 0;
     BGAN_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        for (int v = 0; v < kNumVariants; ++v)
+            BGAN_CUDA_OK(cudaFuncSetAttribute(kVariants[v], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
         attr_dev = dev;
     }
     const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
     const int units = planes * es;  // 128 x 128 channel planes
-    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, x, y, es, units, rule, std_eff, radius, kDefaultPrefetch};
+    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, x, y, es, units, rule, std_eff, radius, kDefaultPrefetch, 0};
+    if (const char* v = getenv("BGAN_TC_DBG")) a.dbg = atoi(v);
     if (const char* v = getenv("BGAN_TC_PF")) a.pf = std::max(0, atoi(v));  // experiments only
     // balanced persistent grid: every CTA runs the same number of rounds (768 planes on 148 SMs -> 128 CTAs x 6 planes
     // rather than 28 CTAs x 6 + 120 x 5), so that the HBM-bound steady state has no latency-bound tail round
@@ -710,13 +1291,8 @@ int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float
     cfg.attrs = attr;
     cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
     int variant = kDefaultVariant;
-    if (const char* v = getenv("BGAN_TC_VARIANT")) variant = atoi(v) & 3;  // experiments only
-    switch (variant) {
-        case 0: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<0>, a, tmap)); break;
-        case 1: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<1>, a, tmap)); break;
-        case 2: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<2>, a, tmap)); break;
-        default: BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<3>, a, tmap)); break;
-    }
+    if (const char* v = getenv("BGAN_TC_VARIANT")) variant = std::min(std::max(atoi(v), 0), kNumVariants - 1);  // experiments only
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kVariants[variant], a, tmap));
     return 0;
 }
 

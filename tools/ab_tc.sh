@@ -1,9 +1,6 @@
-# A/B of the tensor-core blur schedule variants (experiments; see profiles/)
-for v in 0 3; do for pf in 0 1 2 3 5; do
-  echo "=== variant $v pf $pf"
-  BGAN_TC_VARIANT=$v BGAN_TC_PF=$pf python tools/prof_blur.py --stds 5 --iters 300 --sets 6
-done; done > gpurun_out/ab_variants.log 2>&1
-for v in 0 3; do for pf in 1 5; do
-  BGAN_TC_VARIANT=$v BGAN_TC_PF=$pf python tools/trace_tc.py
-done; done > gpurun_out/ab_trace.log 2>&1
+# stage on/off experiments on the two-plane pipeline (results are wrong with a flag set; timing only)
+for d in 0 1 3 4 8 16 32 24 28 60 63; do
+  echo "=== dbg $d"
+  BGAN_TC_VARIANT=12 BGAN_TC_DBG=$d timeout 120 python tools/prof_blur.py --stds 5 --iters 300 --sets 6
+done > gpurun_out/ab_variants.log 2>&1
 cat gpurun_out/ab_variants.log

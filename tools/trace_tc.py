@@ -10,8 +10,10 @@ from blurred_gan_b200 import _lib
 lib = _lib.load()
 n, c, h, w = 256, 3, 128, 128
 std = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
-variant = int(os.environ.get("BGAN_TC_VARIANT", "3"))
-early = bool(variant & 1)
+variant = int(os.environ.get("BGAN_TC_VARIANT", "7"))  # index into kVariants (csrc/blur_tc.cu)
+kv = [0, 1, 2, 3, 4, 5, 6, 7, 14, 15, 23, 31, 0][variant]
+pipe = variant == 12
+early = bool(kv & 1)
 xs = [torch.rand(n, c, h, w, device="cuda") * 2 - 1 for _ in range(4)]
 ys = [torch.empty_like(x) for x in xs]
 trace = torch.zeros(512, dtype=torch.int64, device="cuda")
@@ -40,6 +42,14 @@ for it in range(iters):
         labels += ["it%d   fetch-wait" % it, "it%d   fetch-landed" % it]
     labels.append("it%d converted" % it)
 labels.append("drain")
+if pipe:
+    labels = ["start", "init+alloc", "taps", "chunk-table", "T-built", "prologue", "fetch0-wait", "fetch0-landed", "conv0",
+              "fetch1-wait", "fetch1-landed", "conv1"]
+    for it in range(iters):
+        labels += ["it%d D1 valid" % it, "it%d split" % it]
+        if it + 2 < iters:
+            labels += ["it%d   fetch-wait" % it, "it%d   fetch-landed" % it, "it%d   G1(i+1) done" % it]
+        labels.append("it%d converted(i+2)" % it)
 prev = base
 for i, v in enumerate(st):
     print("%-22s %8d  (+%d)" % (labels[i] if i < len(labels) else "?", v - base, v - prev))
@@ -50,5 +60,10 @@ for name, b, per in (("MMA warp", 128, ["G1 issue", "G1 issued", "G2 issue", "G2
     print("--", name)
     prev = base
     for i, v in enumerate(s2):
-        print("  it%d %-14s %8d  (+%d)" % (i // len(per), per[i % len(per)], v - base, v - prev))
+        if pipe and b == 128:  # G1(0) | G1(1) G2(0) | G1(2) G2(1) | ...
+            lab = ["G1(%d) issue", "G1(%d) issued"][i % 2] % (i // 4 + (1 if i >= 2 else 0)) if (i < 2 or (i - 2) % 4 < 2) and i < 2 + 4 * (iters - 1) \
+                else ["G2(%d) issue", "G2(%d) issued"][i % 2] % ((i - 2) // 4 if i < 2 + 4 * (iters - 1) else iters - 1)
+            print("  %-16s %8d  (+%d)" % (lab, v - base, v - prev))
+        else:
+            print("  it%d %-14s %8d  (+%d)" % (i // len(per), per[i % len(per)], v - base, v - prev))
         prev = v
