@@ -574,11 +574,14 @@ extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int heigh
         g_last_path = 6;
         return blur_axis_launch(x, y, g.planes, g.H, g.Wc, rule, std_eff, radius, taps_device, ws, ws_bytes, stream);
     }
-    if (blur_direct_eligible(g.planes, g.H, g.Wc, g.ES, radius, x, y)) {
+    // 128 x 128 planes: the FFMA kernel up to radius 4 (HBM-bound there); radius 5 costs it 26.8 us per 768 planes against the
+    // tensor-core kernel's 24.7, so it only keeps radius 5 for explicit taps (which the tensor-core kernel does not take)
+    const bool tc_ok = blur_tc_eligible(g.planes, g.H, g.Wc, g.ES, radius, rule, x, y);
+    if (blur_direct_eligible(g.planes, g.H, g.Wc, g.ES, radius, x, y) && !(tc_ok && radius >= 5)) {
         g_last_path = 5;
         return blur_direct_launch(x, y, g.planes, g.ES, radius, rule, std_eff, taps_device, stream);
     }
-    if (blur_tc_eligible(g.planes, g.H, g.Wc, g.ES, radius, rule, x, y)) {
+    if (tc_ok) {
         g_last_path = 4;
         return blur_tc_launch(x, y, g.planes, g.ES, rule, std_eff, radius, stream);
     }

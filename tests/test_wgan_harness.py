@@ -144,10 +144,14 @@ def test_adaptive_controller_tracks_but_does_not_assign_by_default():
 
 
 @pytest.mark.gpu
-def test_celeba_step_on_gpu_matches_the_oracle_blur_step():
+def test_celeba_step_on_gpu_matches_the_oracle_blur_step(monkeypatch):
     """BASELINE configs[2] shape (small batch): the step through the B200 blur == the step through the oracle blur."""
     from blurred_gan_b200.gaussian_blur import GaussianBlur2D
 
+    # the nets run on cuDNN: with TF32 convolutions a 1e-7 difference between the two blurs flips 10-bit roundings and shows up
+    # as ~1e-3 in the scores, so compare the two steps in real fp32
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
     results = []
     for kind in ("b200", "oracle"):
         torch.manual_seed(0)

@@ -1,7 +1,7 @@
 """Print the clock64 phase stamps of CTA 0 of the tensor-core blur kernel (debug aid).
 
 Three timelines: compute thread 0, lane 0 of the MMA warp, lane 0 of the first store warp.
-    BGAN_TC_VARIANT=3 BGAN_TC_PF=2 python tools/trace_tc.py [std]
+    python tools/trace_tc.py [std]
 """
 import os, sys
 import torch
@@ -10,10 +10,7 @@ from blurred_gan_b200 import _lib
 lib = _lib.load()
 n, c, h, w = 256, 3, 128, 128
 std = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
-variant = int(os.environ.get("BGAN_TC_VARIANT", "7"))  # index into kVariants (csrc/blur_tc.cu)
-kv = [0, 1, 2, 3, 4, 5, 6, 7, 14, 15, 23, 31, 0][variant]
-pipe = variant == 12
-early = bool(kv & 1)
+variant, early, pipe = 0, False, True
 xs = [torch.rand(n, c, h, w, device="cuda") * 2 - 1 for _ in range(4)]
 ys = [torch.empty_like(x) for x in xs]
 trace = torch.zeros(512, dtype=torch.int64, device="cuda")
@@ -28,8 +25,8 @@ t = trace.cpu().tolist()
 cnt = t[0]
 st = t[1:1 + cnt]
 base = st[0]
-print("variant %d pf %s: %d stamps; %.0f cycles in %.0f ns -> %.3f GHz" % (
-    variant, os.environ.get("BGAN_TC_PF", "default"), cnt, t[125] - st[0], t[127] - t[126], (t[125] - st[0]) / max(t[127] - t[126], 1)))
+print("%d stamps; %.0f cycles in %.0f ns -> %.3f GHz" % (
+    cnt, t[125] - st[0], t[127] - t[126], (t[125] - st[0]) / max(t[127] - t[126], 1)))
 labels = ["start", "init+alloc", "taps", "chunk-table", "T-copied", "prologue", "fetch0-wait", "fetch0-landed", "first-convert"]
 iters = 6
 for it in range(iters):
