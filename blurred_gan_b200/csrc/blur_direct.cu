@@ -90,6 +90,15 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
             mbar_init(empty + b, C::kGroupWarps);
         }
         mbar_fence_init();
+        // Warm L2 with the first units before waiting for the previous grid (a prefetch only moves DRAM -> L2, where the
+        // previous grid's stores land as well, so it cannot expose stale data): takes the DRAM latency out of the start-up
+        // of back-to-back launches.
+        for (int it = 0; it < n_it && it < kStages; ++it) {
+            const int unit = first + it * stride;
+            const int image = unit / C::kUnitsPerImage, row0 = (unit % C::kUnitsPerImage) * C::kUnitRows - R;
+#pragma unroll
+            for (int p = 0; p < C::kPanels; ++p) tma_prefetch_l2_3d(&tmap, p * C::kPanelFloats - kPad, row0, image);
+        }
     }
     if (a.rule == BGAN_RULE_EXPLICIT) asm volatile("griddepcontrol.wait;" ::: "memory");  // (the taps are read from global memory)
     normalised_taps(a.rule, a.std_eff, R, a.taps_dev, s_g, s_red);  // ends with __syncthreads(): barrier init is visible too
