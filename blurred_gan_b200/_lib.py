@@ -34,6 +34,9 @@ SIGNATURES = {
     "bgan_swd_sort_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "bgan_swd_sort_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "bgan_swd_absdiff_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "bgan_mt19937_randint_i32": (c_int, [c_void_p, POINTER(c_int), c_int64, c_int64, c_int64, c_void_p]),
+    "bgan_swd_positions_i32": (c_int, [c_void_p, POINTER(c_int), c_int, POINTER(c_int), POINTER(c_int), c_int, c_int64, c_int, c_int,
+                                       c_void_p]),
 }
 
 _lib = None

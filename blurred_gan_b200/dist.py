@@ -57,6 +57,52 @@ def positions_for_round(n_images: int, level_sizes, nhood_size: int, nhoods_per_
     return mine
 
 
+def _numpy_mt19937_state():
+    """(address of numpy's global legacy MT19937 state, its lock), or None when the global generator is something else.
+
+    numpy exposes the raw state of a bit generator through its ctypes interface (`state_address`); for MT19937 that is
+    `struct { uint32_t key[624]; int pos; }` (numpy/random/src/mt19937/mt19937.h)."""
+    try:
+        bitgen = np.random.mtrand._rand._bit_generator
+        if type(bitgen).__name__ != "MT19937":
+            return None
+        return int(bitgen.ctypes.state_address), bitgen.lock
+    except Exception:  # an unexpected numpy layout: use numpy's own randint
+        return None
+
+
+def positions_packed_for_round(n_images: int, level_sizes, nhood_size: int, nhoods_per_image: int, rank: int, world: int,
+                               out: np.ndarray | None = None) -> np.ndarray:
+    """`positions_for_round` as one int32 array [level][x | y][n_images * nhoods_per_image] (the layout `API.feed` uploads).
+
+    Same draws from the same stream, but made by `bgan_swd_positions_i32` (csrc/hostrng.cu: a bit-exact replay of
+    numpy's legacy `randint` working in place on numpy's global MT19937 state) -- numpy needs ~10 ns per draw plus ~50 us
+    per call, and every rank of a `world`-rank evaluation replays the draws of all ranks.  Falls back to numpy's own
+    `randint` if the global generator is not the legacy MT19937."""
+    import ctypes
+
+    from . import _lib
+
+    count = nhoods_per_image * n_images
+    levels = len(level_sizes)
+    if out is None:
+        out = np.empty(2 * levels * count, dtype=np.int32)
+    assert out.dtype == np.int32 and out.size == 2 * levels * count and out.flags.c_contiguous
+    state = _numpy_mt19937_state()
+    if state is None:
+        pos = positions_for_round(n_images, level_sizes, nhood_size, nhoods_per_image, rank, world)
+        out[:] = np.concatenate([np.concatenate(p) for p in pos])
+        return out
+    addr, lock = state
+    heights = (ctypes.c_int * levels)(*[int(h) for h, _ in level_sizes])
+    widths = (ctypes.c_int * levels)(*[int(w) for _, w in level_sizes])
+    with lock:
+        rc = _lib.load().bgan_swd_positions_i32(addr, ctypes.cast(addr + 624 * 4, ctypes.POINTER(ctypes.c_int)), levels, heights, widths,
+                                                nhood_size, count, world, rank, out.ctypes.data)
+    _lib.check(rc, "bgan_swd_positions_i32")
+    return out
+
+
 def direction_block(total_dirs: int, rank: int, world: int) -> slice:
     """The block of projection directions (columns of the [dim, repeats * dirs_per_repeat] matrix) owned by `rank`."""
     lo, hi = shard_range(total_dirs, rank, world)

@@ -151,6 +151,30 @@ def reconstruct_laplacian_pyramid(pyramid):
 # ----------------------------------------------------------------------------
 
 
+class _PinnedRing:
+    """A few pinned int32 staging buffers for the per-feed position upload (asynchronous H2D, reused round-robin)."""
+
+    def __init__(self, slots: int = 4):
+        self.bufs = [None] * slots
+        self.events = [None] * slots
+        self.k = 0
+
+    def take(self, n: int):
+        k = self.k = (self.k + 1) % len(self.bufs)
+        if self.events[k] is not None:
+            self.events[k].synchronize()  # the copy that last read this buffer
+        if self.bufs[k] is None or self.bufs[k].numel() < n:
+            self.bufs[k] = torch.empty(n, dtype=torch.int32).pin_memory()
+        return k, self.bufs[k][:n]
+
+    def upload(self, k: int, host: torch.Tensor, device) -> torch.Tensor:
+        dev = host.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[k] = ev
+        return dev
+
+
 class API:
     """``sliced_wasserstein.py:98-133``: begin / feed / end state machine over a Laplacian pyramid.
 
@@ -164,6 +188,7 @@ class API:
         self.device = device
         self.group = group
         self.rank, self.world = _dist.world_info(group) if (distributed or group is not None) else (0, 1)
+        self._stage = None
         # one pyramid level per power of two down to 16 px (image_shape = (C, H, W); H drives it, like the reference)
         self.resolutions = []
         size = image_shape[1]
@@ -190,11 +215,15 @@ class API:
         levels = generate_laplacian_pyramid(mb, len(self.resolutions))
         if self._sums is None:
             self._sums = [torch.zeros(2 * c + 1, dtype=torch.float64, device=mb.device) for _ in levels]
-        # All draws of this feed, in the reference's order (finest level first; x then y), packed into one upload.
-        pos = _dist.positions_for_round(n, [(lv.shape[2], lv.shape[3]) for lv in levels], self.nhood_size, self.nhoods_per_image,
-                                        self.rank, self.world)
+        # All draws of this feed, in the reference's order (finest level first; x then y), written straight into a pinned
+        # staging buffer and uploaded asynchronously.
         count = n * self.nhoods_per_image
-        packed = torch.from_numpy(np.concatenate([np.concatenate(p) for p in pos]).astype(np.int32)).to(mb.device)
+        if self._stage is None:
+            self._stage = _PinnedRing()
+        slot, host = self._stage.take(2 * len(levels) * count)
+        _dist.positions_packed_for_round(n, [(lv.shape[2], lv.shape[3]) for lv in levels], self.nhood_size, self.nhoods_per_image,
+                                         self.rank, self.world, out=host.numpy())
+        packed = self._stage.upload(slot, host, mb.device)
         for lod, level in enumerate(levels):
             px = packed[2 * lod * count : (2 * lod + 1) * count]
             py = packed[(2 * lod + 1) * count : (2 * lod + 2) * count]

@@ -123,6 +123,22 @@ int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws_d
 int bgan_swd_absdiff_sum_f32(const float* a_device, const float* b_device, int64_t count, double* sum_out_device,
                              void* stream);
 
+/* Host-only.  Bit-exact replay of numpy's legacy np.random.randint(low, high, size=count) -- the call behind the patch
+ * positions of sliced_wasserstein.py:20-21 -- on a caller-held MT19937 state: key624 / *pos_inout are the `key` and `pos`
+ * fields of np.random.get_state(), updated in place so that np.random.set_state() continues the same stream.
+ * out_host (count int32, host memory) may be NULL: the stream is advanced and nothing is stored (the draws of other
+ * ranks' minibatches in a multi-rank evaluation).  Ranges are limited to what numpy serves with 32-bit masked rejection
+ * (high - low <= 2^32 - 1) and to int32 results. */
+int bgan_mt19937_randint_i32(uint32_t* key624, int* pos_inout, int64_t low, int64_t high, int64_t count, int32_t* out_host);
+
+/* Host-only.  All patch-position draws of one `feed` round (sliced_wasserstein.py:20-21 as called from :121-123), in the
+ * order a single process feeding the `world` minibatches of this round one after the other would make them: for every
+ * minibatch, for every pyramid level (finest first), `count` columns in [nhood/2, width - nhood/2) then `count` rows in
+ * [nhood/2, height - nhood/2).  The draws of minibatch `rank` are stored as out_host[level][x | y][count] (int32, host
+ * memory, e.g. a pinned staging buffer); the others only advance the stream.  State as in bgan_mt19937_randint_i32. */
+int bgan_swd_positions_i32(uint32_t* key624, int* pos_inout, int levels, const int* heights, const int* widths, int nhood,
+                           int64_t count, int world, int rank, int32_t* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,69 @@ def test_shard_and_direction_helpers():
             covered += list(range(blk.start + lo, blk.start + hi))
     assert covered == list(range(512))
     assert bd.world_info() == (0, 1)
+
+
+# ---- host RNG replay (csrc/hostrng.cu): bit-exact with numpy's legacy randint, in place on numpy's global state ----------
+@pytest.mark.parametrize("low,high,count", [(3, 125, 8192), (3, 61, 8192), (3, 13, 77), (3, 5, 10), (3, 4, 5), (0, 1 << 20, 3000),
+                                            (-5, 7, 100), (3, 125, 65536 * 3 + 17), (3, 125, 0)])
+def test_mt19937_randint_replay_is_numpy_bit_for_bit(low, high, count):
+    import ctypes
+
+    from blurred_gan_b200 import _lib
+
+    lib = _lib.load()
+    for seed in (0, 1, 123):
+        np.random.seed(seed)
+        np.random.randn(3)  # leaves a cached gaussian in the state: must survive
+        want = np.random.randint(low, high, size=(count, 1, 1, 1)).reshape(-1)
+        tail = (np.random.randn(4), np.random.randint(0, 1000, 5))
+        for store in (True, False):
+            np.random.seed(seed)
+            np.random.randn(3)
+            st = np.random.get_state(legacy=True)
+            key, pos = np.array(st[1], dtype=np.uint32, copy=True), ctypes.c_int(int(st[2]))
+            out = np.full(count, -1, dtype=np.int32)
+            rc = lib.bgan_mt19937_randint_i32(key.ctypes.data, ctypes.byref(pos), low, high, count, out.ctypes.data if store else None)
+            assert rc == 0
+            np.random.set_state(("MT19937", key, pos.value, st[3], st[4]))
+            if store:
+                assert np.array_equal(out, want)
+            got_tail = (np.random.randn(4), np.random.randint(0, 1000, 5))
+            assert np.array_equal(got_tail[0], tail[0]) and np.array_equal(got_tail[1], tail[1])  # the stream continues identically
+
+
+def test_mt19937_randint_argument_errors():
+    import ctypes
+
+    from blurred_gan_b200 import _lib
+
+    lib = _lib.load()
+    key, pos = np.zeros(624, dtype=np.uint32), ctypes.c_int(624)
+    out = np.zeros(4, dtype=np.int32)
+    assert lib.bgan_mt19937_randint_i32(key.ctypes.data, ctypes.byref(pos), 5, 5, 4, out.ctypes.data) == -1  # low >= high
+    assert lib.bgan_mt19937_randint_i32(key.ctypes.data, ctypes.byref(pos), 0, 1 << 33, 4, out.ctypes.data) == -3  # 64-bit path of numpy
+    pos = ctypes.c_int(700)
+    assert lib.bgan_mt19937_randint_i32(key.ctypes.data, ctypes.byref(pos), 0, 5, 4, out.ctypes.data) == -1
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 1), (3, 0), (8, 5)])
+def test_packed_positions_equal_the_numpy_draws(world, rank):
+    from blurred_gan_b200 import dist as bd
+
+    sizes = [(128, 128), (64, 64), (32, 48), (16, 16)]
+    np.random.seed(7)
+    ref = bd.positions_for_round(5, sizes, 7, 128, rank, world)
+    ref_tail = np.random.randn(3)
+    np.random.seed(7)
+    got = bd.positions_packed_for_round(5, sizes, 7, 128, rank, world)
+    got_tail = np.random.randn(3)
+    assert got.dtype == np.int32
+    assert np.array_equal(got, np.concatenate([np.concatenate(p) for p in ref]))
+    assert np.array_equal(ref_tail, got_tail)
+    # a global generator that is not the legacy MT19937 falls back to numpy's own randint
+    import unittest.mock as mock
+
+    with mock.patch.object(bd, "_numpy_mt19937_state", return_value=None):
+        np.random.seed(7)
+        again = bd.positions_packed_for_round(5, sizes, 7, 128, rank, world)
+    assert np.array_equal(again, got)
