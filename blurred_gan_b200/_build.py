@@ -16,7 +16,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libbgan_b200.so")
-SOURCES = ["capi.cu", "blur.cu", "blur_tc.cu", "blur_direct.cu", "blur_axis.cu", "swd.cu", "sort.cu", "hostrng.cu"]
+SOURCES = ["capi.cu", "blur.cu", "blur_tc.cu", "blur_direct.cu", "blur_axis.cu", "swd.cu", "project_tc.cu", "sort.cu", "hostrng.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

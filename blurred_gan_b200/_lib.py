@@ -31,6 +31,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p]),
     "bgan_swd_normalise_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_double, c_void_p]),
     "bgan_swd_project_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "bgan_swd_project_last_path": (c_int, []),
     "bgan_swd_sort_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "bgan_swd_sort_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "bgan_swd_absdiff_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -284,8 +284,22 @@ extern "C" int bgan_swd_normalise_f32(float* desc, int64_t rows, int c, int per_
     return 0;
 }
 
+namespace bgan {
+// project_tc.cu: tcgen05 path (descriptor length <= 192)
+bool project_tc_eligible(int64_t rows, int k, int d);
+int project_tc_launch(const float* desc, int64_t rows, int k, const float* dirs, int d, float* proj, cudaStream_t stream);
+}  // namespace bgan
+
+static thread_local int g_project_path = 0;
+extern "C" int bgan_swd_project_last_path(void) { return g_project_path; }
+
 extern "C" int bgan_swd_project_f32(const float* desc, int64_t rows, int k, const float* dirs, int d, float* proj_out, void* stream) {
     BGAN_REQUIRE(desc && dirs && proj_out && rows > 0 && k > 0 && d > 0, BGAN_E_BADARG, "bgan_swd_project_f32: bad arguments");
+    if (project_tc_eligible(rows, k, d)) {
+        g_project_path = 2;
+        return project_tc_launch(desc, rows, k, dirs, d, proj_out, static_cast<cudaStream_t>(stream));
+    }
+    g_project_path = 1;
     const size_t smem = sizeof(float) * (static_cast<size_t>(kPM) * (k | 1) + static_cast<size_t>(k) * kPN);
     BGAN_REQUIRE(smem <= 227 * 1024, BGAN_E_UNSUPPORTED, "bgan_swd_project_f32: descriptor length %d too large", k);
     BGAN_REQUIRE(ceil_div64(rows, kPM) < (int64_t(1) << 31), BGAN_E_BADARG, "too many rows");

@@ -113,6 +113,9 @@ int bgan_swd_normalise_f32(float* desc_device, int64_t rows, int c, int per_chan
  * desc [rows, k] row-major, dirs [k, d] row-major -> proj_out [d, rows]. */
 int bgan_swd_project_f32(const float* desc_device, int64_t rows, int k, const float* dirs_device, int d,
                          float* proj_out_device, void* stream);
+/* How the last bgan_swd_project_f32 call on this thread was executed: 1 = FP32 FFMA kernel, 2 = tcgen05 kernel
+ * (error-compensated fp16 split, k <= 192). */
+int bgan_swd_project_last_path(void);
 
 /* sliced_wasserstein.py:47-48  ascending sort of each of the `segments` contiguous runs of `rows`
  * floats, in place (LSD radix sort; ws from the query below). */

@@ -83,6 +83,45 @@ def test_projection(rows, k, d):
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
 
 
+@pytest.mark.parametrize("rows,k,d", [(20000, 147, 512), (333, 192, 70), (1000, 16, 128), (257, 1, 1)])
+def test_projection_tensor_core_path_any_magnitude(rows, k, d, monkeypatch):
+    """The tcgen05 projection (csrc/project_tc.cu): rows of very different magnitudes (per-row power-of-two scales), zero
+    rows, ragged last tile, direction counts that are not multiples of 128 -- against fp64 and against the FFMA kernel."""
+    from blurred_gan_b200 import _lib, ops
+
+    rs = np.random.RandomState(rows + k)
+    A = rs.randn(rows, k).astype(np.float32)
+    A[1::7] *= 1e-6
+    A[2::7] *= 3e4
+    A[3::11] = 0.0
+    A[:, 0] *= 1e-3
+    dirs = (rs.randn(k, d) * 0.07).astype(np.float32)
+    want = (A.astype(np.float64) @ dirs.astype(np.float64)).T
+    got = ops.swd_project(_dev(A), _dev(dirs)).cpu().numpy()
+    assert _lib.load().bgan_swd_project_last_path() == 2
+    monkeypatch.setenv("BGAN_SWD_NO_TC_PROJECT", "1")
+    fma = ops.swd_project(_dev(A), _dev(dirs)).cpu().numpy()
+    assert _lib.load().bgan_swd_project_last_path() == 1
+    monkeypatch.delenv("BGAN_SWD_NO_TC_PROJECT")
+    # per row (= per output column): error relative to that row's largest projection
+    scale = np.abs(want).max(axis=0, keepdims=True) + 1e-30
+    assert (np.abs(got - want) / scale).max() <= 1e-5
+    assert (np.abs(fma - want) / scale).max() <= 1e-5
+    assert np.all(got[:, 3::11] == 0.0)
+
+
+def test_projection_long_descriptors_use_the_fma_kernel():
+    from blurred_gan_b200 import _lib, ops
+
+    rs = np.random.RandomState(5)
+    A = rs.randn(300, 200).astype(np.float32)
+    dirs = rs.randn(200, 40).astype(np.float32)
+    got = ops.swd_project(_dev(A), _dev(dirs)).cpu().numpy()
+    assert _lib.load().bgan_swd_project_last_path() == 1
+    want = (A.astype(np.float64) @ dirs.astype(np.float64)).T
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
 @pytest.mark.parametrize("segments,rows", [(1, 1), (3, 5), (2, 4096), (5, 4097), (130, 1000), (4, 100000), (1, 1 << 20)])
 def test_segmented_sort_is_exact(segments, rows):
     from blurred_gan_b200 import ops
