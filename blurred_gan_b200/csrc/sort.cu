@@ -2,12 +2,15 @@
 // sliced_wasserstein.py:47-48, one segment per projection direction (direction-major layout).
 //
 // 4 passes of 8-bit digits over order-preserving uint32 images of the floats.  Per pass:
-//   hist    : per-(segment, tile) digit counts                       -> counts[seg][digit][tile]
-//   scan    : exclusive prefix over (digit-major, tile-minor)        -> same array, in place
-//   scatter : stable rank inside the tile (warp match_any + per-warp counters), keys regrouped by
+//   hist    : per-(segment, tile) digit counts                       -> counts[seg][tile][digit]
+//   scan    : exclusive prefix over (digit-major, tile-minor)        -> offsets[seg][tile][digit] (two small kernels)
+//   scatter : stable rank inside the tile (lanes with equal digits found by eight ballots -- match_any for the top
+//             byte, which takes few distinct values -- plus per-warp counters), keys regrouped by
 //             digit in shared memory, then written as coalesced runs to their global positions.
 // Tile = 256 threads x 16 keys.  The float<->uint transform is fused into the first load and the
 // last store, so the sort runs in place from the caller's point of view (ping-pong through ws).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace bgan {
@@ -28,123 +31,184 @@ __device__ __forceinline__ uint32_t load_key(const uint32_t* __restrict__ p) {
     return FIRST ? float_to_ordered(v) : v;
 }
 
-// counts[(seg * 256 + digit) * tiles + tile]
-template <bool FIRST>
+// counts[(seg * tiles + tile) * 256 + digit]: one coalesced 1 KB row per tile, for the histogram's write and the
+// scatter's read alike
+// lanes of the warp that hold the same 8-bit digit (bit 8 set = padding lane, matches nobody real).
+// MATCH: one match_any -- fast when a 32-key row holds a handful of distinct digits (the top byte of the keys: sign and
+// exponent), but its cost grows with the number of distinct values (measured: ~240 cycles per row for uniform digits).
+// Otherwise eight ballots, one per digit bit: constant time.
+template <bool MATCH>
+__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t d) {
+    if constexpr (MATCH) {
+        return __match_any_sync(0xffffffffu, d);
+    } else {
+        uint32_t peers = __ballot_sync(0xffffffffu, d < 256u);
+        if (d >= 256u) peers = ~peers;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+        }
+        return peers;
+    }
+}
+
+template <bool FIRST, bool MATCH>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t rows, int tiles, int shift,
                                                                   uint32_t* __restrict__ counts) {
     __shared__ uint32_t s_cnt[kSortWarps][kRadix];
     const int tile = blockIdx.x, seg = blockIdx.y;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kSortWarps * kRadix / 4; i += kSortThreads) reinterpret_cast<uint4*>(&s_cnt[0][0])[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const uint32_t* src = keys + static_cast<size_t>(seg) * rows;
-    const int64_t base = static_cast<int64_t>(tile) * kTile;
+    const uint32_t* src = keys + static_cast<size_t>(seg) * rows + static_cast<size_t>(tile) * kTile;
+    const int valid = (rows - static_cast<int64_t>(tile) * kTile < kTile) ? static_cast<int>(rows - static_cast<int64_t>(tile) * kTile) : kTile;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // MATCH (top byte: a handful of distinct digits per 32-key row): one shared-memory atomic per distinct digit;
+    // otherwise (digits close to uniform: conflicts are rare) one atomic per key
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
-        const int64_t idx = base + i * kSortThreads + tid;
-        if (idx < rows) atomicAdd(&s_cnt[warp][(load_key<FIRST>(src + idx) >> shift) & 0xff], 1u);
+        const int local = i * kSortThreads + tid;
+        const bool ok = local < valid;
+        const uint32_t d = ok ? (load_key<FIRST>(src + local) >> shift) & 0xff : 256u;
+        if constexpr (MATCH) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (ok && (peers & lt_mask) == 0) atomicAdd(&s_cnt[warp][d], static_cast<uint32_t>(__popc(peers)));
+        } else {
+            if (ok) atomicAdd(&s_cnt[warp][d], 1u);
+        }
     }
+    (void)lt_mask;
     __syncthreads();
-    if (tid < kRadix) {
-        uint32_t total = 0;
+    uint32_t total = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) total += s_cnt[w][tid];
-        counts[(static_cast<size_t>(seg) * kRadix + tid) * tiles + tile] = total;
-    }
+    for (int w = 0; w < kSortWarps; ++w) total += s_cnt[w][tid];
+    counts[(static_cast<size_t>(seg) * tiles + tile) * kRadix + tid] = total;
 }
 
-// one CTA per segment: exclusive scan of counts[seg][0 .. 256*tiles)
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ counts, int tiles) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    uint32_t* c = counts + static_cast<size_t>(blockIdx.x) * kRadix * tiles;
-    const int n = kRadix * tiles;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int lo = tid * per, hi = min(n, lo + per);
-    uint32_t local = 0;
-    for (int i = lo; i < hi; ++i) local += c[i];
-    // block-wide exclusive scan of `local`
-    uint32_t incl = local;
+// Offsets: counts[seg][tile][digit] -> global start of every (digit, tile) run, i.e. the exclusive prefix in (digit-major,
+// tile-minor) order, written to a second array of the same shape.  Two small kernels over (chunk of tiles, segment) CTAs of 256 threads
+// (thread = digit; every access is a coalesced 1 KB row):
+//   partial : part[seg][chunk][digit] = sum of the chunk's counts
+//   offsets : digit totals -> exclusive scan over the digits -> start of this chunk -> walk the chunk
+constexpr int kScanChunkTiles = 16;  // tiles per chunk (fully unrolled loads)
+constexpr int kMaxScanChunks = 1024;
+
+__global__ void __launch_bounds__(kRadix) radix_scan_partial_kernel(const uint32_t* __restrict__ counts, int tiles, int chunks,
+                                                                    uint32_t* __restrict__ part) {
+    const int chunk = blockIdx.x, seg = blockIdx.y, d = threadIdx.x;
+    const int per = (tiles + chunks - 1) / chunks;
+    const int t0 = min(chunk * per, tiles), t1 = min(t0 + per, tiles);
+    const uint32_t* c = counts + static_cast<size_t>(seg) * tiles * kRadix + d;
+    uint32_t sum = 0;
+#pragma unroll 8
+    for (int t = t0; t < t1; ++t) sum += __ldg(c + static_cast<size_t>(t) * kRadix);
+    part[(static_cast<size_t>(seg) * chunks + chunk) * kRadix + d] = sum;
+}
+
+__global__ void __launch_bounds__(kRadix) radix_scan_offsets_kernel(const uint32_t* __restrict__ counts, int tiles, int chunks,
+                                                                    const uint32_t* __restrict__ part, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t s_warp[kRadix / 32];
+    const int chunk = blockIdx.x, seg = blockIdx.y, d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const uint32_t* p = part + static_cast<size_t>(seg) * chunks * kRadix + d;
+    uint32_t total = 0, before = 0;  // this digit: all chunks / the chunks in front of mine
+    for (int ch = 0; ch < chunks; ++ch) {
+        const uint32_t v = __ldg(p + static_cast<size_t>(ch) * kRadix);
+        total += v;
+        if (ch < chunk) before += v;
+    }
+    uint32_t incl = total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t v = s_warp[lane], iv = v;
+    uint32_t run = incl - total + before;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+    const int per = (tiles + chunks - 1) / chunks;
+    const int t0 = min(chunk * per, tiles), t1 = min(t0 + per, tiles);
+    // out of place (reads and writes provably do not alias: all loads of the chunk are in flight together)
+    const uint32_t* c = counts + static_cast<size_t>(seg) * tiles * kRadix + d;
+    uint32_t* o = offsets + static_cast<size_t>(seg) * tiles * kRadix + d;
+    for (int tb = t0; tb < t1; tb += 8) {
+        uint32_t v[8];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= o) iv += t;
+        for (int j = 0; j < 8; ++j) v[j] = tb + j < t1 ? __ldg(c + static_cast<size_t>(tb + j) * kRadix) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (tb + j < t1) o[static_cast<size_t>(tb + j) * kRadix] = run;
+            run += v[j];
         }
-        s_warp[lane] = iv - v;
     }
-    __syncthreads();
-    uint32_t run = s_warp[warp] + incl - local;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t v = c[i];
-        c[i] = run;
-        run += v;
-    }
-    (void)s_carry;
 }
 
-template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
-                                                                     int64_t rows, int tiles, int shift,
-                                                                     const uint32_t* __restrict__ offsets) {
-    __shared__ uint32_t s_cnt[kSortWarps][kRadix];   // per-warp digit counts, then per-warp exclusive prefixes
-    __shared__ uint32_t s_tile_start[kRadix];        // first local slot of each digit inside the tile
-    __shared__ uint32_t s_gbase[kRadix];             // global position of the tile's first key of each digit
-    __shared__ uint32_t s_keys[kTile];
-    __shared__ uint32_t s_scan[kSortWarps];
+// Scatter of one tile.  Ranking: per 32-key row, lanes with the same digit find each other with match_any; the lowest one
+// bumps the warp's counter of that digit (one shared-memory atomic per distinct digit) and hands the old value to its
+// peers.  Keys are then regrouped by digit in shared memory and leave as runs of consecutive addresses.
+struct ScatterSmem {
+    uint32_t cnt[kSortWarps][kRadix];  // per-warp digit counts, then: first local slot of the warp's keys of that digit
+    uint32_t gdelta[kRadix];           // global position of the tile's first key of a digit - its first local slot
+    uint32_t keys[kTile];
+    uint32_t scan[kSortWarps];
+};
 
+template <bool FIRST, bool LAST, bool FULL, bool MATCH>
+__device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+                                             int64_t rows, int tiles, int shift, const uint32_t* __restrict__ offsets) {
+    auto& s_cnt = sm.cnt;
+    auto& s_gdelta = sm.gdelta;
+    auto& s_keys = sm.keys;
+    auto& s_scan = sm.scan;
     const int tile = blockIdx.x, seg = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
-    if (tid < kRadix) s_gbase[tid] = offsets[(static_cast<size_t>(seg) * kRadix + tid) * tiles + tile];
+    for (int i = tid; i < kSortWarps * kRadix / 4; i += kSortThreads) reinterpret_cast<uint4*>(&s_cnt[0][0])[i] = make_uint4(0, 0, 0, 0);
+    const uint32_t gbase = offsets[(static_cast<size_t>(seg) * tiles + tile) * kRadix + tid];
     __syncthreads();
 
-    const uint32_t* src = keys_in + static_cast<size_t>(seg) * rows;
-    uint32_t* dst = keys_out + static_cast<size_t>(seg) * rows;
     const int64_t tile_base = static_cast<int64_t>(tile) * kTile;
-    const int valid = (rows - tile_base < kTile) ? static_cast<int>(rows - tile_base) : kTile;
+    const uint32_t* src = keys_in + static_cast<size_t>(seg) * rows + tile_base;
+    uint32_t* dst = keys_out + static_cast<size_t>(seg) * rows;
+    const int valid = FULL ? kTile : static_cast<int>(rows - tile_base);  // (FULL == false: 1 .. kTile - 1)
     const int warp_base = warp * (kItems * 32);  // each warp owns 512 consecutive keys -> stability
+    uint32_t* my_cnt = s_cnt[warp];
 
     uint32_t key[kItems];
-    uint16_t rank[kItems];
+    uint32_t rank2[kItems / 2];  // two 16-bit ranks per register (a rank is < 4096)
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
         const int local = warp_base + i * 32 + lane;
-        const bool ok = local < valid;
-        key[i] = ok ? load_key<FIRST>(src + tile_base + local) : 0xffffffffu;
-        const uint32_t d = (key[i] >> shift) & 0xff;
+        const bool ok = FULL || local < valid;
+        key[i] = ok ? load_key<FIRST>(src + local) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const bool ok = FULL || warp_base + i * 32 + lane < valid;
         // lanes holding padding keys vote with digit 256 so that they never disturb a real digit
-        const uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : 256u);
+        const uint32_t d = ok ? (key[i] >> shift) & 0xff : 256u;
+        const uint32_t peers = same_digit_lanes<MATCH>(d);
+        const int leader = __ffs(peers) - 1;
+        // the lowest lane of every group bumps the warp's counter of that digit (groups hold different digits, so plain
+        // read + write; the __syncwarp makes it visible to whichever lane leads that digit in the next row)
         uint32_t before = 0;
-        if (ok) before = s_cnt[warp][d];
+        if (lane == leader && ok) {
+            before = my_cnt[d];
+            my_cnt[d] = before + __popc(peers);
+        }
         __syncwarp();
-        if (ok && (peers & lt_mask) == 0) s_cnt[warp][d] = before + __popc(peers);
-        __syncwarp();
-        rank[i] = static_cast<uint16_t>(before + __popc(peers & lt_mask));
+        before = __shfl_sync(0xffffffffu, before, leader);
+        const uint32_t r = before + __popc(peers & lt_mask);
+        rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r << 16)) : r;
     }
     __syncthreads();
 
-    // per digit: exclusive prefix over warps, tile total
+    // per digit (thread = digit): exclusive prefix over warps, tile total, then the exclusive scan of the totals
     uint32_t digit_total = 0;
-    if (tid < kRadix) {
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            const uint32_t c = s_cnt[w][tid];
-            s_cnt[w][tid] = digit_total;
-            digit_total += c;
-        }
-    }
-    // exclusive scan of digit totals over the 256 digits (threads 0..255 = all threads)
+    for (int w = 0; w < kSortWarps; ++w) digit_total += s_cnt[w][tid];
     uint32_t incl = digit_total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -153,34 +217,51 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
     }
     if (lane == 31) s_scan[warp] = incl;
     __syncthreads();
-    uint32_t warp_off = 0;
+    uint32_t tile_start = incl - digit_total;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w)
-        if (w < warp) warp_off += s_scan[w];
-    if (tid < kRadix) s_tile_start[tid] = warp_off + incl - digit_total;
+        if (w < warp) tile_start += s_scan[w];
+    s_gdelta[tid] = gbase - tile_start;
+    {
+        uint32_t run = tile_start;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = s_cnt[w][tid];
+            s_cnt[w][tid] = run;
+            run += c;
+        }
+    }
     __syncthreads();
 
     // regroup by digit in shared memory
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
-        const int local = warp_base + i * 32 + lane;
-        if (local < valid) {
-            const uint32_t d = (key[i] >> shift) & 0xff;
-            s_keys[s_tile_start[d] + s_cnt[warp][d] + rank[i]] = key[i];
-        }
+        if (FULL || warp_base + i * 32 + lane < valid)
+            s_keys[my_cnt[(key[i] >> shift) & 0xff] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffff)] = key[i];
     }
     __syncthreads();
 
-    // coalesced runs out to global
+    // runs of consecutive addresses out to global
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
         const int slot = i * kSortThreads + tid;
-        if (slot < valid) {
+        if (FULL || slot < valid) {
             const uint32_t k = s_keys[slot];
-            const uint32_t d = (k >> shift) & 0xff;
-            dst[s_gbase[d] + (slot - s_tile_start[d])] = LAST ? ordered_to_float(k) : k;
+            dst[s_gdelta[(k >> shift) & 0xff] + slot] = LAST ? ordered_to_float(k) : k;
         }
     }
+}
+
+template <bool FIRST, bool LAST, bool MATCH>
+__global__ void __launch_bounds__(kSortThreads, 4) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
+                                                                     int64_t rows, int tiles, int shift,
+                                                                     const uint32_t* __restrict__ offsets) {
+    __shared__ ScatterSmem sm;
+    // complete tiles run without any bounds logic; only the last tile of a segment can be ragged
+    if ((static_cast<int64_t>(blockIdx.x) + 1) * kTile <= rows)
+        scatter_tile<FIRST, LAST, true, MATCH>(sm, keys_in, keys_out, rows, tiles, shift, offsets);
+    else
+        scatter_tile<FIRST, LAST, false, MATCH>(sm, keys_in, keys_out, rows, tiles, shift, offsets);
 }
 
 }  // namespace
@@ -188,12 +269,17 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
 
 using namespace bgan;
 
+static int scan_chunks(int64_t tiles) {
+    return static_cast<int>(std::min<int64_t>(kMaxScanChunks, std::max<int64_t>(1, ceil_div64(tiles, kScanChunkTiles))));
+}
+
 extern "C" size_t bgan_swd_sort_workspace_bytes(int64_t rows, int segments) {
     if (rows <= 0 || segments <= 0) return 0;
     const int64_t tiles = ceil_div64(rows, kTile);
     const size_t keys = static_cast<size_t>(rows) * segments * sizeof(uint32_t);
     const size_t counts = static_cast<size_t>(segments) * kRadix * tiles * sizeof(uint32_t);
-    return ((keys + 255) & ~size_t(255)) + counts;
+    const size_t part = static_cast<size_t>(segments) * kRadix * scan_chunks(tiles) * sizeof(uint32_t);
+    return ((keys + 255) & ~size_t(255)) + 2 * counts + part;  // keys | counts | offsets | chunk partials
 }
 
 extern "C" int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws, size_t ws_bytes, void* stream_) {
@@ -208,24 +294,32 @@ extern "C" int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments,
     uint32_t* a = reinterpret_cast<uint32_t*>(keys_device);
     uint32_t* b = static_cast<uint32_t*>(ws);
     uint32_t* counts = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + keys_bytes);
+    const int chunks = scan_chunks(tiles);
+    uint32_t* offsets = counts + static_cast<size_t>(segments) * kRadix * tiles;
+    uint32_t* part = offsets + static_cast<size_t>(segments) * kRadix * tiles;
+    dim3 scan_grid(chunks, segments);
+    auto scan = [&]() {
+        radix_scan_partial_kernel<<<scan_grid, kRadix, 0, stream>>>(counts, tiles, chunks, part);
+        radix_scan_offsets_kernel<<<scan_grid, kRadix, 0, stream>>>(counts, tiles, chunks, part, offsets);
+    };
     dim3 grid(tiles, segments);
 
     // pass 0: a -> b (float -> ordered uint on load)
-    radix_hist_kernel<true><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 0, counts);
-    radix_scan_kernel<<<segments, 1024, 0, stream>>>(counts, tiles);
-    radix_scatter_kernel<true, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 0, counts);
+    radix_hist_kernel<true, false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 0, counts);
+    scan();
+    radix_scatter_kernel<true, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 0, offsets);
     // pass 1: b -> a
-    radix_hist_kernel<false><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 8, counts);
-    radix_scan_kernel<<<segments, 1024, 0, stream>>>(counts, tiles);
-    radix_scatter_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 8, counts);
+    radix_hist_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 8, counts);
+    scan();
+    radix_scatter_kernel<false, false, false><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 8, offsets);
     // pass 2: a -> b
-    radix_hist_kernel<false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 16, counts);
-    radix_scan_kernel<<<segments, 1024, 0, stream>>>(counts, tiles);
-    radix_scatter_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 16, counts);
+    radix_hist_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 16, counts);
+    scan();
+    radix_scatter_kernel<false, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 16, offsets);
     // pass 3: b -> a (ordered uint -> float on store)
-    radix_hist_kernel<false><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 24, counts);
-    radix_scan_kernel<<<segments, 1024, 0, stream>>>(counts, tiles);
-    radix_scatter_kernel<false, true><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 24, counts);
+    radix_hist_kernel<false, true><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 24, counts);
+    scan();
+    radix_scatter_kernel<false, true, true><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 24, offsets);
     BGAN_LAUNCH_OK();
     return 0;
 }

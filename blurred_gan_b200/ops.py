@@ -220,8 +220,8 @@ def swd_normalise_(desc: torch.Tensor, sums: torch.Tensor, count: float) -> torc
     return desc
 
 
-def swd_project(desc: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
-    """desc [rows, k] @ dirs [k, d] -> direction-major [d, rows]."""
+def swd_project(desc: torch.Tensor, dirs: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """desc [rows, k] @ dirs [k, d] -> direction-major [d, rows] (into ``out`` when given)."""
     _require_cuda(desc, "swd_project")
     _require_cuda(dirs, "swd_project(dirs)")
     desc = desc.contiguous()
@@ -229,15 +229,18 @@ def swd_project(desc: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
     rows, k = desc.shape
     assert dirs.shape[0] == k
     d = dirs.shape[1]
-    out = torch.empty((d, rows), dtype=torch.float32, device=desc.device)
+    if out is None:
+        out = torch.empty((d, rows), dtype=torch.float32, device=desc.device)
+    assert out.shape == (d, rows) and out.dtype == torch.float32 and out.is_contiguous() and out.device == desc.device
     with _on_device(desc.device):
         rc = _lib.load().bgan_swd_project_f32(desc.data_ptr(), rows, k, dirs.data_ptr(), d, out.data_ptr(), _stream_ptr())
     _lib.check(rc, "bgan_swd_project_f32")
     return out
 
 
-def swd_sort_(keys: torch.Tensor) -> torch.Tensor:
-    """Ascending in-place sort of every row of keys [segments, rows]."""
+def swd_sort_(keys: torch.Tensor, scratch: dict | None = None) -> torch.Tensor:
+    """Ascending in-place sort of every row of keys [segments, rows].  ``scratch``: a dict in which the workspace tensor is
+    kept between calls (an evaluation sorts 32 equally shaped arrays)."""
     _require_cuda(keys, "swd_sort_")
     assert keys.is_contiguous() and keys.dim() == 2
     segments, rows = keys.shape
@@ -247,7 +250,11 @@ def swd_sort_(keys: torch.Tensor) -> torch.Tensor:
         while done < segments:  # the kernel grid caps segments per launch
             seg = min(segments - done, 32768)
             ws_bytes = lib.bgan_swd_sort_workspace_bytes(rows, seg)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+            ws = scratch.get("sort_ws") if scratch is not None else None
+            if ws is None or ws.numel() < ws_bytes or ws.device != keys.device:
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+                if scratch is not None:
+                    scratch["sort_ws"] = ws
             part = keys[done : done + seg]
             _lib.check(lib.bgan_swd_sort_f32(part.data_ptr(), rows, seg, ws.data_ptr(), ws_bytes, _stream_ptr()), "bgan_swd_sort_f32")
             done += seg

@@ -77,11 +77,22 @@ def _draw_directions(dim, dirs_per_repeat):
     return dirs.astype(np.float32)
 
 
-def sliced_wasserstein(A, B, dir_repeats, dirs_per_repeat, group=None):
+def _scratch_proj(scratch, name, d, rows, device):
+    if scratch is None:
+        return None
+    t = scratch.get(name)
+    if t is None or t.shape != (d, rows) or t.device != device:
+        t = scratch[name] = torch.empty((d, rows), dtype=torch.float32, device=device)
+    return t
+
+
+def sliced_wasserstein(A, B, dir_repeats, dirs_per_repeat, group=None, scratch=None):
     """``sliced_wasserstein.py:38-51``: mean over repeats of mean |sort(A dirs) - sort(B dirs)|.
 
     With a process group, A and B are the full (already all-gathered) descriptor sets on every rank and each rank
-    handles its own block of the ``dir_repeats * dirs_per_repeat`` directions; the per-repeat sums are all-reduced."""
+    handles its own block of the ``dir_repeats * dirs_per_repeat`` directions; the per-repeat sums are all-reduced.
+    ``scratch`` (a dict, optional): the two projection arrays and the sort workspace are kept in it between calls --
+    ``API.end`` evaluates every pyramid level with equally shaped arrays."""
     A = _to_device(A)
     B = _to_device(B, A.device)
     assert A.dim() == 2 and A.shape == B.shape  # (neighborhood, descriptor_component)
@@ -93,8 +104,10 @@ def sliced_wasserstein(A, B, dir_repeats, dirs_per_repeat, group=None):
     partial = torch.zeros(dir_repeats, dtype=torch.float64, device=A.device)
     if block.stop > block.start:
         dirs_t = torch.from_numpy(np.ascontiguousarray(dirs[:, block])).to(A.device)
-        projA = ops.swd_sort_(ops.swd_project(A, dirs_t))  # [directions of this rank, rows], each row sorted
-        projB = ops.swd_sort_(ops.swd_project(B, dirs_t))
+        nd = block.stop - block.start
+        # [directions of this rank, rows], each row sorted
+        projA = ops.swd_sort_(ops.swd_project(A, dirs_t, out=_scratch_proj(scratch, "projA", nd, rows, A.device)), scratch)
+        projB = ops.swd_sort_(ops.swd_project(B, dirs_t, out=_scratch_proj(scratch, "projB", nd, rows, A.device)), scratch)
         for rep, lo, hi in _dist.repeat_segments(block, dirs_per_repeat):
             partial[rep : rep + 1] += ops.swd_absdiff_sum(projA[lo:hi], projB[lo:hi])
     return np.float32(_dist.combine_repeat_sums(partial, rows, dirs_per_repeat, group))
@@ -251,7 +264,9 @@ class API:
                     np.random.randn(d.shape[1], self.dirs_per_repeat)
             dist = [np.float32(0.0)] * len(desc)
         else:
-            dist = [sliced_wasserstein(real, fake, self.dir_repeats, self.dirs_per_repeat, self.group)
+            scratch = {}  # projections + sort workspace, shared by the levels of this evaluation
+            dist = [sliced_wasserstein(real, fake, self.dir_repeats, self.dirs_per_repeat, self.group, scratch)
                     for real, fake in zip(self.desc_real, desc)]
+            del scratch
         scaled = [d * 1e3 for d in dist]
         return scaled + [np.mean(scaled)]
