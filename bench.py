@@ -431,19 +431,26 @@ def run_native(args, stds):
         e2e_steps = max(2, min(args.steps, 5))
         for _ in range(2):
             e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize(dev)  # (all three streams)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        # three windows of e2e_steps steps, the median window is reported: the pipeline is driven by the host (copies, module
+        # calls, the autograd thread), and a single hiccup of a shared host otherwise decides the number
+        windows = []
+        for _ in range(3):
+            barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize(dev)  # (all three streams)
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            windows.append(dt)
+        dt = sorted(windows)[1]
         e2e = {"value": world * e2e_steps * images_per_step / dt, "unit": "images/s",
                "h2d_bytes_per_step": 2 * plane_bytes * len(stds), "d2h_bytes_per_step": 2 * plane_bytes * len(stds),
-               "steps": e2e_steps, "api": "GaussianBlur(std)(x); y.backward(g); pinned host x, g -> host y, grad_x; H2D | blur | D2H on three streams"}
+               "steps": e2e_steps, "windows_s": [round(w, 4) for w in windows], "api": "GaussianBlur(std)(x); y.backward(g); pinned host x, g -> host y, grad_x; H2D | blur | D2H on three streams"}
         launches += 0  # e2e launches are outside the timed `value` region
 
     line = {
