@@ -310,6 +310,34 @@ def test_tensor_core_path_matches_oracle_and_fma_path(std, monkeypatch):
     assert_close(got_tf, bo.blur_images_tf_ref(xt, std), "tensor-core path, tf rule, std=%g" % std)
 
 
+@pytest.mark.parametrize("planes", [1, 2, 3, 147, 148, 149, 297, 445, 600])
+def test_tensor_core_pipeline_plane_counts(planes):
+    """The two-planes-in-flight pipeline of blur_tc128_kernel has separate code for the first, second and later planes of a
+    CTA and a balanced grid (ceil(planes / rounds) CTAs): 1, 2, 3, 4 and 5 planes per CTA, with and without a short CTA.
+    Every plane has its own magnitude (per-plane power-of-two scales travel through a 4-deep ring).  Checked against the
+    CUDA-core path (itself checked against the oracle), bit pattern of the plane order included."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    torch.manual_seed(planes)
+    x = torch.rand(planes, 1, 128, 128, device="cuda") * 2 - 1
+    x *= torch.logspace(-4, 4, planes, device="cuda").view(-1, 1, 1, 1)[torch.randperm(planes, device="cuda")]
+    mod = GaussianBlur(5.0).cuda()
+    got = mod(x)
+    assert ops.last_blur_path() == 4
+    os.environ["BGAN_BLUR_NO_TC"] = "1"
+    try:
+        ref = mod(x)
+        assert ops.last_blur_path() in (1, 2)
+    finally:
+        os.environ.pop("BGAN_BLUR_NO_TC", None)
+    err = (got - ref).abs().amax(dim=(1, 2, 3)) / ref.abs().amax(dim=(1, 2, 3))
+    assert err.max().item() <= 1e-5, "plane %d of %d: %g" % (int(err.argmax()), planes, err.max().item())
+    # one oracle check on top (first and last plane)
+    for n in (0, planes - 1):
+        assert_close(got[n:n + 1], bo.gaussian_blur_torch_ref(x[n:n + 1].cpu().numpy(), 5.0), "plane %d of %d" % (n, planes))
+
+
 @pytest.mark.parametrize("std", [0.5, 3.0, 23.0])
 def test_tensor_core_path_nhwc(std, monkeypatch):
     """NHWC 128 x 128 x 3 (the layout of the reference's Keras layer): TMA deinterleaves with element stride 3."""
