@@ -24,6 +24,9 @@ SIGNATURES = {
     "bgan_blur2d_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "bgan_blur2d_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
+    "bgan_blur2d_multi_f32": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "bgan_lerp_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "bgan_blur2d_last_path": (c_int, []),
     "bgan_pyr_down_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "bgan_pyr_up_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -31,7 +31,7 @@ namespace bgan {
 
 // blur_tc.cu: tcgen05 path for 128 x 128 planes
 bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, const float* x, const float* y);
-int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream);
+int blur_tc_launch(const MultiIO& io, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream);
 
 // blur_axis.cu: two-pass tensor-core path for large planes and wide blurs
 bool blur_axis_shape_ok(int planes, int H, int W, int ES, int radius);
@@ -41,7 +41,7 @@ int blur_axis_launch(const float* x, float* y, int planes, int H, int W, int rul
                      size_t ws_bytes, cudaStream_t stream);
 // blur_direct.cu: FFMA path for 128 x 128 images and radius <= 4
 bool blur_direct_eligible(int planes, int H, int Wc, int ES, int radius, const float* x, const float* y);
-int blur_direct_launch(const float* x, float* y, int planes, int es, int radius, int rule, float std_eff, const float* taps_dev,
+int blur_direct_launch(const MultiIO& io, int planes, int es, int radius, int rule, float std_eff, const float* taps_dev,
                        cudaStream_t stream);
 
 namespace {
@@ -555,41 +555,71 @@ extern "C" size_t bgan_blur2d_workspace_bytes(int n, int c, int height, int widt
 
 extern "C" int bgan_blur2d_last_path(void) { return g_last_path; }
 
-extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int height, int width, int layout, int rule,
-                               float std_eff, int radius, const float* taps_device, void* ws, size_t ws_bytes, void* stream_) {
-    Geometry g;
-    BGAN_REQUIRE(geometry(n, c, height, width, layout, &g), BGAN_E_BADARG,
-                 "bgan_blur2d_f32: bad shape/layout (n=%d c=%d h=%d w=%d layout=%d)", n, c, height, width, layout);
-    BGAN_REQUIRE(x && y && x != y, BGAN_E_BADARG, "bgan_blur2d_f32: x and y must be distinct non-null device pointers");
-    BGAN_REQUIRE(radius >= 0, BGAN_E_BADARG, "bgan_blur2d_f32: negative radius");
-    BGAN_REQUIRE(rule == BGAN_RULE_TORCH || rule == BGAN_RULE_TF || (rule == BGAN_RULE_EXPLICIT && taps_device), BGAN_E_BADARG,
-                 "bgan_blur2d_f32: unknown rule %d or missing taps", rule);
-    BGAN_REQUIRE(rule == BGAN_RULE_EXPLICIT || std_eff > 0.0f, BGAN_E_BADARG, "bgan_blur2d_f32: std must be positive");
-    BGAN_REQUIRE(static_cast<int64_t>(g.planes) * g.H * g.Wc < (int64_t(1) << 40), BGAN_E_BADARG, "tensor too large");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    bool tma = false;
+namespace bgan {
+namespace {
 
-    if (blur_axis_eligible(g.planes, g.H, g.Wc, g.ES, radius, x, y) && ws != nullptr &&
-        ws_bytes >= blur_axis_workspace_bytes(g.planes, g.H, g.Wc) && reinterpret_cast<uintptr_t>(ws) % 16 == 0) {
-        g_last_path = 6;
-        return blur_axis_launch(x, y, g.planes, g.H, g.Wc, rule, std_eff, radius, taps_device, ws, ws_bytes, stream);
+// out[i][:] = u[i][:] + a[i] * (v[i][:] - u[i][:]): the interpolates of the gradient penalty (wgan.py:237-239) taken
+// between two *blurred* batches -- the blur is linear, so B(x_hat) = B(reals) + a (B(fakes) - B(reals)) and the third
+// forward blur of the critic step is this HBM-bound elementwise pass instead (12 bytes per element).
+__global__ void __launch_bounds__(256) lerp_rows_kernel(const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ a,
+                                                        float* __restrict__ out, int64_t per_row4, int64_t total4) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const float w = __ldg(a + i / per_row4);
+        const float4 p = __ldcs(reinterpret_cast<const float4*>(u) + i), q = __ldcs(reinterpret_cast<const float4*>(v) + i);
+        __stcs(reinterpret_cast<float4*>(out) + i,
+               make_float4(p.x + w * (q.x - p.x), p.y + w * (q.y - p.y), p.z + w * (q.z - p.z), p.w + w * (q.w - p.w)));
     }
+}
+__global__ void __launch_bounds__(256) lerp_rows_scalar_kernel(const float* __restrict__ u, const float* __restrict__ v,
+                                                               const float* __restrict__ a, float* __restrict__ out, int64_t per_row,
+                                                               int64_t total) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float w = __ldg(a + i / per_row), p = u[i];
+        out[i] = p + w * (v[i] - p);
+    }
+}
+
+// One tensor (io.count == 1) or several equally shaped ones.  The 128 x 128 kernels take all tensors in one launch;
+// every other shape falls back to one launch sequence per tensor (same stream, so the scratch is reused).
+int blur2d_dispatch(const MultiIO& io, const Geometry& g, int rule, float std_eff, int radius, const float* taps_device, void* ws,
+                    size_t ws_bytes, cudaStream_t stream) {
+    bool tma = false;
+    bool tc_ok = true, direct_ok = true, axis_ok = true;
+    for (int t = 0; t < io.count; ++t) {
+        tc_ok = tc_ok && blur_tc_eligible(g.planes, g.H, g.Wc, g.ES, radius, rule, io.x[t], io.y[t]);
+        direct_ok = direct_ok && blur_direct_eligible(g.planes, g.H, g.Wc, g.ES, radius, io.x[t], io.y[t]);
+        axis_ok = axis_ok && blur_axis_eligible(g.planes, g.H, g.Wc, g.ES, radius, io.x[t], io.y[t]);
+    }
+    if (axis_ok && ws != nullptr && ws_bytes >= blur_axis_workspace_bytes(g.planes, g.H, g.Wc) && reinterpret_cast<uintptr_t>(ws) % 16 == 0) {
+        g_last_path = 6;
+        for (int t = 0; t < io.count; ++t) {
+            const int rc = blur_axis_launch(io.x[t], io.y[t], g.planes, g.H, g.Wc, rule, std_eff, radius, taps_device, ws, ws_bytes, stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    // the unit counters of the one-launch kernels are 32-bit
+    const bool one_launch = static_cast<int64_t>(g.planes) * g.ES * io.count * 2 < (int64_t(1) << 31);
     // 128 x 128 planes: the FFMA kernel up to radius 4 (HBM-bound there); radius 5 costs it 26.8 us per 768 planes against the
     // tensor-core kernel's 24.7, so it only keeps radius 5 for explicit taps (which the tensor-core kernel does not take)
-    const bool tc_ok = blur_tc_eligible(g.planes, g.H, g.Wc, g.ES, radius, rule, x, y);
-    if (blur_direct_eligible(g.planes, g.H, g.Wc, g.ES, radius, x, y) && !(tc_ok && radius >= 5)) {
+    if (one_launch && direct_ok && !(tc_ok && radius >= 5)) {
         g_last_path = 5;
-        return blur_direct_launch(x, y, g.planes, g.ES, radius, rule, std_eff, taps_device, stream);
+        return blur_direct_launch(io, g.planes, g.ES, radius, rule, std_eff, taps_device, stream);
     }
-    if (tc_ok) {
+    if (one_launch && tc_ok) {
         g_last_path = 4;
-        return blur_tc_launch(x, y, g.planes, g.ES, rule, std_eff, radius, stream);
+        return blur_tc_launch(io, g.planes, g.ES, rule, std_eff, radius, stream);
     }
     Plan fused = choose_plan(g.H, g.Wc, g.ES, radius, radius);
     if (fused.ok) {
-        int rc = launch_any(fused, g.ES, x, y, g.planes, rule, std_eff, taps_device, stream, &tma);
+        for (int t = 0; t < io.count; ++t) {
+            const int rc = launch_any(fused, g.ES, io.x[t], io.y[t], g.planes, rule, std_eff, taps_device, stream, &tma);
+            if (rc) return rc;
+        }
         g_last_path = tma ? 1 : 2;
-        return rc;
+        return 0;
     }
     // halo too large for one tile: row pass and column pass as two launches through scratch
     const size_t need = static_cast<size_t>(g.planes) * g.H * g.Wc * sizeof(float);
@@ -599,9 +629,77 @@ extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int heigh
     Plan colp = choose_plan(g.H, g.Wc, g.ES, 0, radius);
     BGAN_REQUIRE(rowp.ok && colp.ok, BGAN_E_UNSUPPORTED, "bgan_blur2d_f32: radius %d too large for shared memory", radius);
     float* mid = static_cast<float*>(ws);
-    int rc = launch_any(rowp, g.ES, x, mid, g.planes, rule, std_eff, taps_device, stream, &tma);
-    if (rc) return rc;
-    rc = launch_any(colp, g.ES, mid, y, g.planes, rule, std_eff, taps_device, stream, &tma);
+    for (int t = 0; t < io.count; ++t) {
+        int rc = launch_any(rowp, g.ES, io.x[t], mid, g.planes, rule, std_eff, taps_device, stream, &tma);
+        if (rc) return rc;
+        rc = launch_any(colp, g.ES, mid, io.y[t], g.planes, rule, std_eff, taps_device, stream, &tma);
+        if (rc) return rc;
+    }
     g_last_path = 3;
-    return rc;
+    return 0;
+}
+
+int blur2d_check(const char* who, const Geometry& g, int rule, float std_eff, int radius, const float* taps_device) {
+    BGAN_REQUIRE(radius >= 0, BGAN_E_BADARG, "%s: negative radius", who);
+    BGAN_REQUIRE(rule == BGAN_RULE_TORCH || rule == BGAN_RULE_TF || (rule == BGAN_RULE_EXPLICIT && taps_device), BGAN_E_BADARG,
+                 "%s: unknown rule %d or missing taps", who, rule);
+    BGAN_REQUIRE(rule == BGAN_RULE_EXPLICIT || std_eff > 0.0f, BGAN_E_BADARG, "%s: std must be positive", who);
+    BGAN_REQUIRE(static_cast<int64_t>(g.planes) * g.H * g.Wc < (int64_t(1) << 40), BGAN_E_BADARG, "tensor too large");
+    return 0;
+}
+
+}  // namespace
+}  // namespace bgan
+
+extern "C" int bgan_blur2d_f32(const float* x, float* y, int n, int c, int height, int width, int layout, int rule,
+                               float std_eff, int radius, const float* taps_device, void* ws, size_t ws_bytes, void* stream_) {
+    Geometry g;
+    BGAN_REQUIRE(geometry(n, c, height, width, layout, &g), BGAN_E_BADARG,
+                 "bgan_blur2d_f32: bad shape/layout (n=%d c=%d h=%d w=%d layout=%d)", n, c, height, width, layout);
+    BGAN_REQUIRE(x && y && x != y, BGAN_E_BADARG, "bgan_blur2d_f32: x and y must be distinct non-null device pointers");
+    if (const int rc = blur2d_check("bgan_blur2d_f32", g, rule, std_eff, radius, taps_device)) return rc;
+    MultiIO io{};
+    io.x[0] = x;
+    io.y[0] = y;
+    io.count = 1;
+    return blur2d_dispatch(io, g, rule, std_eff, radius, taps_device, ws, ws_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int bgan_blur2d_multi_f32(const float* const* xs, float* const* ys, int count, int n, int c, int height, int width, int layout,
+                                     int rule, float std_eff, int radius, const float* taps_device, void* ws, size_t ws_bytes,
+                                     void* stream_) {
+    Geometry g;
+    BGAN_REQUIRE(geometry(n, c, height, width, layout, &g), BGAN_E_BADARG,
+                 "bgan_blur2d_multi_f32: bad shape/layout (n=%d c=%d h=%d w=%d layout=%d)", n, c, height, width, layout);
+    BGAN_REQUIRE(xs && ys && count >= 1 && count <= kMaxMulti, BGAN_E_BADARG, "bgan_blur2d_multi_f32: 1 .. %d tensors per call, got %d",
+                 kMaxMulti, count);
+    if (const int rc = blur2d_check("bgan_blur2d_multi_f32", g, rule, std_eff, radius, taps_device)) return rc;
+    MultiIO io{};
+    io.count = count;
+    for (int t = 0; t < count; ++t) {
+        io.x[t] = xs[t];
+        io.y[t] = ys[t];
+        BGAN_REQUIRE(xs[t] && ys[t], BGAN_E_BADARG, "bgan_blur2d_multi_f32: null pointer for tensor %d", t);
+        for (int u = 0; u < count; ++u)
+            BGAN_REQUIRE(ys[t] != xs[u] && (u == t || ys[t] != ys[u]), BGAN_E_BADARG,
+                         "bgan_blur2d_multi_f32: output %d aliases another tensor of the call", t);
+    }
+    return blur2d_dispatch(io, g, rule, std_eff, radius, taps_device, ws, ws_bytes, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int bgan_lerp_rows_f32(const float* u, const float* v, const float* weights, float* out, int64_t rows, int64_t per_row,
+                                  void* stream_) {
+    BGAN_REQUIRE(u && v && weights && out && rows >= 0 && per_row >= 1, BGAN_E_BADARG, "bgan_lerp_rows_f32: bad arguments");
+    if (rows == 0) return 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t total = rows * per_row;
+    const bool vec = per_row % 4 == 0 && (reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+    const int64_t work = vec ? total / 4 : total;
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(ceil_div64(work, 256), static_cast<int64_t>(device_sm_count()) * 8));
+    if (vec)
+        lerp_rows_kernel<<<grid, 256, 0, stream>>>(u, v, weights, out, per_row / 4, work);
+    else
+        lerp_rows_scalar_kernel<<<grid, 256, 0, stream>>>(u, v, weights, out, per_row, work);
+    BGAN_LAUNCH_OK();
+    return 0;
 }

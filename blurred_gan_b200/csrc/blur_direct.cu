@@ -56,15 +56,19 @@ struct DirectCfg {
 };
 
 struct DirectArgs {
-    float* y;
+    float* y[kMaxMulti];  // one output per tensor of a multi-tensor launch (bgan_blur2d_multi_f32)
     const float* taps_dev;
-    int units;  // planes (NCHW) or 2 * images (NHWC)
+    int units;             // all tensors together: planes (NCHW) or 2 * images (NHWC), tensor after tensor
+    int units_per_tensor;
     int rule;
     float std_eff;
 };
+struct DirectMaps {
+    CUtensorMap m[kMaxMulti];
+};
 
 template <int ES, int R>
-__global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const DirectArgs a, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const DirectArgs a, const __grid_constant__ DirectMaps maps) {
     using C = DirectCfg<ES>;
     constexpr int kTaps = 2 * R + 1;
     constexpr int kLaneFloats = 4 * ES;      // floats of one row owned by a lane (4 pixels)
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
-        tma_prefetch_desc(&tmap);
+        tma_prefetch_desc(&maps.m[0]);
         for (int b = 0; b < kStages; ++b) {
             mbar_init(full + b, 1);
             mbar_init(empty + b, C::kGroupWarps);
@@ -94,10 +98,11 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
         // previous grid's stores land as well, so it cannot expose stale data): takes the DRAM latency out of the start-up
         // of back-to-back launches.
         for (int it = 0; it < n_it && it < kStages; ++it) {
-            const int unit = first + it * stride;
+            int unit = first + it * stride;
+            const CUtensorMap* tmap = &maps.m[multi_locate(unit, a.units_per_tensor)];
             const int image = unit / C::kUnitsPerImage, row0 = (unit % C::kUnitsPerImage) * C::kUnitRows - R;
 #pragma unroll
-            for (int p = 0; p < C::kPanels; ++p) tma_prefetch_l2_3d(&tmap, p * C::kPanelFloats - kPad, row0, image);
+            for (int p = 0; p < C::kPanels; ++p) tma_prefetch_l2_3d(tmap, p * C::kPanelFloats - kPad, row0, image);
         }
     }
     if (a.rule == BGAN_RULE_EXPLICIT) asm volatile("griddepcontrol.wait;" ::: "memory");  // (the taps are read from global memory)
@@ -110,13 +115,14 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
             for (int it = 0; it < n_it; ++it) {
                 const int b = it % kStages, use = it / kStages;
                 if (use > 0) mbar_wait(empty + b, (use - 1) & 1);
-                const int unit = first + it * stride;
+                int unit = first + it * stride;
+                const CUtensorMap* tmap = &maps.m[multi_locate(unit, a.units_per_tensor)];
                 const int image = unit / C::kUnitsPerImage, row0 = (unit % C::kUnitsPerImage) * C::kUnitRows - R;
                 unsigned char* dst = smem + b * C::stage_bytes(R);
                 mbar_arrive_expect_tx(full + b, static_cast<uint32_t>(C::box_rows(R) * kPitch * C::kPanels * sizeof(float)));
 #pragma unroll
                 for (int p = 0; p < C::kPanels; ++p)
-                    tma_load_3d(dst + p * C::panel_bytes(R), &tmap, full + b, p * C::kPanelFloats - kPad, row0, image);
+                    tma_load_3d(dst + p * C::panel_bytes(R), tmap, full + b, p * C::kPanelFloats - kPad, row0, image);
             }
         }
         return;
@@ -133,11 +139,12 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
     const int group = warp / C::kGroupWarps, gwarp = warp % C::kGroupWarps;
     for (int it = group; it < n_it; it += C::kGroups) {
         const int b = it % kStages, use = it / kStages;
-        const int unit = first + it * stride;
+        int unit = first + it * stride;
+        float* const y = multi_pick(a.y, multi_locate(unit, a.units_per_tensor));
         const int image = unit / C::kUnitsPerImage, out_row0 = (unit % C::kUnitsPerImage) * C::kUnitRows + gwarp * C::kRowsPerWarp;
         mbar_wait(full + b, use & 1);
         const float* src = reinterpret_cast<const float*>(smem + b * C::stage_bytes(R)) + lane_off + gwarp * C::kRowsPerWarp * kPitch;
-        float* dst = a.y + (static_cast<size_t>(image) * kD + out_row0) * C::kRowFloats + lane * kLaneFloats;
+        float* dst = y + (static_cast<size_t>(image) * kD + out_row0) * C::kRowFloats + lane * kLaneFloats;
 
         float hrow[kRows][kLaneFloats];  // horizontally blurred rows; only 2r + 1 of them are live at any time
 #pragma unroll
@@ -216,10 +223,10 @@ EncodeTiledFn direct_encode_fn() {
 }
 
 template <int ES, int R>
-int launch_direct(const float* x, float* y, int images, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
+int launch_direct(const MultiIO& io, int images, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
     using C = DirectCfg<ES>;
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
+    DirectMaps maps;
+    memset(&maps, 0, sizeof(maps));
     thread_local bool bound = false;  // cuTensorMapEncodeTiled needs a context bound to the calling thread
     if (!bound) {
         cudaFree(nullptr);
@@ -229,10 +236,13 @@ int launch_direct(const float* x, float* y, int images, int rule, float std_eff,
     const cuuint64_t strides[2] = {static_cast<cuuint64_t>(C::kRowFloats) * 4, static_cast<cuuint64_t>(C::kRowFloats) * kD * 4};
     const cuuint32_t box[3] = {static_cast<cuuint32_t>(C::pitch(R)), static_cast<cuuint32_t>(C::box_rows(R)), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult res = direct_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
-                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);  // out-of-bounds rows read as zeros
-    BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
+    for (int t = 0; t < io.count; ++t) {
+        const CUresult res = direct_encode_fn()(&maps.m[t], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(io.x[t]), dims, strides, box,
+                                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);  // out-of-bounds rows read as zeros
+        BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
+    }
     auto kernel = blur_direct128_kernel<ES, R>;
     thread_local int attr_dev = -1;
     int dev = 0;
@@ -241,8 +251,8 @@ int launch_direct(const float* x, float* y, int images, int rule, float std_eff,
         BGAN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::smem_bytes(R))));
         attr_dev = dev;
     }
-    const int units = images * C::kUnitsPerImage;
-    DirectArgs a{y, taps_dev, units, rule, std_eff};
+    const int per_tensor = images * C::kUnitsPerImage, units = per_tensor * io.count;
+    DirectArgs a{{io.y[0], io.y[1], io.y[2], io.y[3]}, taps_dev, units, per_tensor, rule, std_eff};
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(static_cast<unsigned>(std::min(units, device_sm_count())));
@@ -255,22 +265,22 @@ int launch_direct(const float* x, float* y, int images, int rule, float std_eff,
     const char* no_pdl = getenv("BGAN_BLUR_NO_PDL");
     cfg.attrs = attr;
     cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
-    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, tmap));
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, maps));
     return 0;
 }
 
 template <int ES>
-int launch_direct_r(const float* x, float* y, int images, int radius, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
+int launch_direct_r(const MultiIO& io, int images, int radius, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
     switch (radius) {
-        case 1: return launch_direct<ES, 1>(x, y, images, rule, std_eff, taps_dev, stream);
-        case 2: return launch_direct<ES, 2>(x, y, images, rule, std_eff, taps_dev, stream);
-        case 3: return launch_direct<ES, 3>(x, y, images, rule, std_eff, taps_dev, stream);
-        case 4: return launch_direct<ES, 4>(x, y, images, rule, std_eff, taps_dev, stream);
+        case 1: return launch_direct<ES, 1>(io, images, rule, std_eff, taps_dev, stream);
+        case 2: return launch_direct<ES, 2>(io, images, rule, std_eff, taps_dev, stream);
+        case 3: return launch_direct<ES, 3>(io, images, rule, std_eff, taps_dev, stream);
+        case 4: return launch_direct<ES, 4>(io, images, rule, std_eff, taps_dev, stream);
         default: break;
     }
     if constexpr (ES == 1) {
         switch (radius) {
-            case 5: return launch_direct<ES, 5>(x, y, images, rule, std_eff, taps_dev, stream);
+            case 5: return launch_direct<ES, 5>(io, images, rule, std_eff, taps_dev, stream);
             default: break;
         }
     }
@@ -296,10 +306,11 @@ bool blur_direct_eligible(int planes, int H, int Wc, int ES, int radius, const f
            reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 && direct_encode_fn() != nullptr;
 }
 
-int blur_direct_launch(const float* x, float* y, int planes, int es, int radius, int rule, float std_eff, const float* taps_dev,
+// `planes` per tensor; io.count equally shaped tensors are blurred by one launch
+int blur_direct_launch(const MultiIO& io, int planes, int es, int radius, int rule, float std_eff, const float* taps_dev,
                        cudaStream_t stream) {
-    return es == 1 ? launch_direct_r<1>(x, y, planes, radius, rule, std_eff, taps_dev, stream)
-                   : launch_direct_r<3>(x, y, planes, radius, rule, std_eff, taps_dev, stream);
+    return es == 1 ? launch_direct_r<1>(io, planes, radius, rule, std_eff, taps_dev, stream)
+                   : launch_direct_r<3>(io, planes, radius, rule, std_eff, taps_dev, stream);
 }
 
 }  // namespace bgan

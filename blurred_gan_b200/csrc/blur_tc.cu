@@ -65,12 +65,17 @@ constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) <<
 // named barriers: X(i) tiles ready (even / odd plane), compute-warp internal, Z(i) ready (4 + i % 2)
 constexpr int kBarA0 = 1, kBarFetch = 2, kBarA1 = 3, kBarB0 = 4;
 
+struct TcMaps {
+    CUtensorMap m[kMaxMulti];
+};
+
 struct TcArgs {
     long long* trace;  // debug: clock64 stamps of CTA 0 (nullptr in production), see tools/trace_tc.py
-    const float* x;    // only read directly for es > 1 (es == 1 goes through the tensor map)
-    float* y;
+    const float* x[kMaxMulti];  // only read directly for es > 1 (es == 1 goes through the tensor maps)
+    float* y[kMaxMulti];        // one (x, y) pair per tensor of a multi-tensor launch (bgan_blur2d_multi_f32)
     int es;  // 1: planes are contiguous [128][128]; 3: NHWC, plane p = channel p % 3 of image p / 3 (interleaved floats)
-    int planes;
+    int planes;             // all tensors together, numbered tensor after tensor
+    int planes_per_tensor;
     int rule;
     float std_eff;
     int radius;
@@ -220,7 +225,7 @@ __device__ __forceinline__ void gather_plane_load(unsigned char* stage, const fl
 //
 // The tensor pipe never waits for the split (it works on the next plane's GEMM1 meanwhile) and the compute warps never
 // hold the next plane in registers across the split.  Operand conventions: see the top of the file.
-__global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ TcMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
     float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
-        tma_prefetch_desc(&tmap);
+        tma_prefetch_desc(&maps.m[0]);
         mbar_init(mbar_tma, a.es == 1 ? 1 : kTcThreads);
         mbar_init(mbar_g1 + 0, 1);
         mbar_init(mbar_g1 + 1, 1);
@@ -260,12 +265,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             // Pull the first two planes into L2 *before* waiting for the previous grid: a prefetch only moves DRAM -> L2, and L2
             // is where the previous grid's stores land, so it can never expose stale data -- but it takes the DRAM latency
             // (~2.8 us when all CTAs ask at once) out of the pipeline fill of back-to-back launches.
-            tma_prefetch_l2_3d(&tmap, 0, 0, static_cast<int>(blockIdx.x));
-            if (blockIdx.x + gridDim.x < static_cast<unsigned>(a.planes))
-                tma_prefetch_l2_3d(&tmap, 0, 0, static_cast<int>(blockIdx.x + gridDim.x));
+            int p0 = static_cast<int>(blockIdx.x), p1 = static_cast<int>(blockIdx.x + gridDim.x);
+            const CUtensorMap* m0 = &maps.m[multi_locate(p0, a.planes_per_tensor)];
+            tma_prefetch_l2_3d(m0, 0, 0, p0);
+            if (blockIdx.x + gridDim.x < static_cast<unsigned>(a.planes)) {
+                const CUtensorMap* m1 = &maps.m[multi_locate(p1, a.planes_per_tensor)];
+                tma_prefetch_l2_3d(m1, 0, 0, p1);
+            }
             asm volatile("griddepcontrol.wait;" ::: "memory");
             mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-            tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, static_cast<int>(blockIdx.x));
+            tma_load_3d(smem + kOffStage, m0, mbar_tma, 0, 0, p0);
         }
     }
     __syncwarp();
@@ -289,7 +298,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     __syncthreads();
     if (a.es != 1 && warp < kTcWarps) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        gather_plane_load(smem + kOffStage, a.x, mbar_tma, static_cast<int>(blockIdx.x), a.es, tid);
+        int p0 = static_cast<int>(blockIdx.x);
+        const float* x0 = multi_pick(a.x, multi_locate(p0, a.planes_per_tensor));
+        gather_plane_load(smem + kOffStage, x0, mbar_tma, p0, a.es, tid);
     }
     stamp();  // taps
     uint4* s_chi = reinterpret_cast<uint4*>(smem + kOffO1);
@@ -383,12 +394,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         // ================= store warps: D2 = Y^T -> registers -> global, coalesced along w' ===========================
         const int c0 = ((warp - kStoreWarp0) >> 2) * 64;  // first D2 column (= output row h') of this warp
         for (int i = 0; i < n; ++i) {
-            const int p = first + i * stride;
+            int p = first + i * stride;
+            float* const y = multi_pick(a.y, multi_locate(p, a.planes_per_tensor));
             mbar_wait(mbar_g2, i & 1);
             tc_fence_after();
             if (warp == kStoreWarp0) stamp_role(256);  // G2(i) complete
             const float inv = s_inv[i & 3];
-            float* q = a.y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
+            float* q = y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
             const size_t ld = static_cast<size_t>(kP) * a.es;  // floats between consecutive output rows h'
             q += static_cast<size_t>(c0) * ld;
             float o0[32], o1[32];
@@ -433,11 +445,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             if (lane == 0) s_max[buf * kTcWarps + warp] = m;
             named_bar_sync(kBarFetch, kTcThreads);
             if (a.es != 1) {
-                if (next_plane < a.planes) gather_plane_load(smem + kOffStage, a.x, mbar_tma, next_plane, a.es, tid);
+                if (next_plane < a.planes) {
+                    int pn = next_plane;
+                    const float* xn = multi_pick(a.x, multi_locate(pn, a.planes_per_tensor));
+                    gather_plane_load(smem + kOffStage, xn, mbar_tma, pn, a.es, tid);
+                }
             } else if (tid == 0 && next_plane < a.planes) {
+                int pn = next_plane, pa = next_plane + stride;
                 mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-                tma_load_3d(smem + kOffStage, &tmap, mbar_tma, 0, 0, next_plane);
-                if (next_plane + stride < a.planes) tma_prefetch_l2_3d(&tmap, 0, 0, next_plane + stride);  // warm L2 one more ahead
+                tma_load_3d(smem + kOffStage, &maps.m[multi_locate(pn, a.planes_per_tensor)], mbar_tma, 0, 0, pn);
+                if (next_plane + stride < a.planes)  // warm L2 one more ahead
+                    tma_prefetch_l2_3d(&maps.m[multi_locate(pa, a.planes_per_tensor)], 0, 0, pa);
             }
         };
         auto convert = [&](int buf, int it_of_plane) {
@@ -565,9 +583,10 @@ bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, c
 }
 
 // `planes` counts geometry planes: N*C for NCHW (es = 1), N images of 128 x 384 interleaved floats for NHWC (es = 3)
-int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
+// (per tensor; io.count equally shaped tensors are blurred by one launch)
+int blur_tc_launch(const MultiIO& io, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
     bind_primary_context();
     // the tensor map is only used for es == 1; for NHWC it describes the same memory as dense 128-float rows (never loaded)
     const cuuint64_t rows = static_cast<cuuint64_t>(planes) * es;
@@ -575,10 +594,12 @@ int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float
     const cuuint64_t strides[2] = {kP * 4, kP * kP * 4};
     const cuuint32_t box[3] = {kP, kP, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult res = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
+    for (int t = 0; t < io.count; ++t) {
+        const CUresult res = encode_fn()(&maps.m[t], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(io.x[t]), dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
+    }
     thread_local int attr_dev = -1;
     int dev = 0;
     BGAN_CUDA_OK(cudaGetDevice(&dev));
@@ -587,8 +608,11 @@ int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float
         attr_dev = dev;
     }
     const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
-    const int units = planes * es;  // 128 x 128 channel planes
-    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr, x, y, es, units, rule, std_eff, radius};
+    const int per_tensor = planes * es, units = per_tensor * io.count;  // 128 x 128 channel planes
+    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr,
+             {io.x[0], io.x[1], io.x[2], io.x[3]},
+             {io.y[0], io.y[1], io.y[2], io.y[3]},
+             es, units, per_tensor, rule, std_eff, radius};
     // balanced persistent grid: every CTA runs the same number of rounds (768 planes on 148 SMs -> 128 CTAs x 6 planes
     // rather than 28 CTAs x 6 + 120 x 5), so that the HBM-bound steady state has no latency-bound tail round
     const int sms = device_sm_count();
@@ -610,7 +634,7 @@ int blur_tc_launch(const float* x, float* y, int planes, int es, int rule, float
     const char* no_pdl = getenv("BGAN_BLUR_NO_PDL");
     cfg.attrs = attr;
     cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
-    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel, a, tmap));
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel, a, maps));
     return 0;
 }
 

@@ -36,6 +36,15 @@ int device_max_smem_optin();
 // Check the launch itself (not its completion): the ABI is asynchronous.
 #define BGAN_LAUNCH_OK() BGAN_CUDA_OK(cudaGetLastError())
 
+// Several equally shaped tensors blurred by ONE launch of the 128 x 128 kernels (bgan_blur2d_multi_f32: the critic step's
+// real and generated batches).  Work units are numbered tensor after tensor.
+constexpr int kMaxMulti = 4;
+struct MultiIO {
+    const float* x[kMaxMulti];
+    float* y[kMaxMulti];
+    int count;
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
@@ -57,6 +66,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// unit -> (tensor, unit inside the tensor) for a multi-tensor launch; `per` units per tensor, at most kMaxMulti tensors
+__device__ __forceinline__ int multi_locate(int& unit, int per) {
+    int t = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxMulti; ++k) {
+        if (unit >= per) {
+            unit -= per;
+            ++t;
+        }
+    }
+    return t;
+}
+// p[t] of a kernel-parameter array without dynamic indexing (which would copy the array to local memory)
+template <typename T>
+__device__ __forceinline__ T multi_pick(T const (&p)[kMaxMulti], int t) {
+    return t == 0 ? p[0] : t == 1 ? p[1] : t == 2 ? p[2] : p[3];
 }
 
 // mbarrier + TMA (cp.async.bulk.tensor) primitives, written as the PTX they are.

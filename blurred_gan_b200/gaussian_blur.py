@@ -89,6 +89,25 @@ def blur_images(images: torch.Tensor, scale) -> torch.Tensor:
     return gaussian_blur(images, std, kernel_size)
 
 
+def blur_images_many(images, scale) -> list:
+    """``[blur_images(x, scale) for x in images]`` for 1 .. 4 equally shaped batches through ONE call of the library
+    (one launch for 128 x 128 planes).  Not in the reference: its critic step blurs the generated and the real batch back
+    to back with the same sigma (``wgan.py:136-137`` through ``blurred_gan.py:30-35``); SURVEY section 8f, row N3."""
+    images = list(images)
+    for x in images:
+        if not torch.is_tensor(x) or x.dim() != 4:
+            raise RuntimeError("blur_images_many expects 4-D tensors")
+        if not x.is_cuda:
+            raise RuntimeError("blur_images_many (blurred_gan_b200) runs on CUDA tensors only; there is no CPU fallback")
+    h, w, _ = get_image_dims(images[0])
+    kernel_size = _F32(appropriate_kernel_size(scale))
+    kernel_size = min(max(kernel_size, _F32(3.0)), _F32(max(h, w)))
+    std = max(_F32(appropriate_std(kernel_size)), _F32(0.01))
+    data_format = get_data_format(images[0])
+    layout = ops.LAYOUT_NHWC if data_format == "NHWC" else ops.LAYOUT_NCHW
+    return list(ops.blur2d_multi(images, layout, ops.RULE_TF, float(_as_f32(std)), int(kernel_size) // 2))
+
+
 class GaussianBlur2D(nn.Module):
     """``gaussian_blur.py:135-148``.  ``std`` is a non-trainable scalar that sigma controllers overwrite
     every batch (reference callbacks.py:60-62); it is kept as a frozen Parameter so that it
@@ -115,3 +134,7 @@ class GaussianBlur2D(nn.Module):
 
     def forward(self, image: torch.Tensor) -> torch.Tensor:
         return blur_images(image, self.std_value())
+
+    def forward_many(self, *images: torch.Tensor) -> list:
+        """The layer applied to several equally shaped batches in one library call (see ``blur_images_many``)."""
+        return blur_images_many(images, self.std_value())

@@ -8,6 +8,9 @@ itself applied to the incoming gradient.  That covers the 7 blur applications of
 """
 from __future__ import annotations
 
+import ctypes
+from typing import Sequence
+
 import numpy as np
 import torch
 
@@ -100,6 +103,77 @@ def _blur2d_setup(ctx, inputs, output):
 
 
 blur2d.register_autograd(_blur2d_backward, setup_context=_blur2d_setup)
+
+
+MAX_MULTI = 4  # kMaxMulti of csrc/common.cuh: tensors per bgan_blur2d_multi_f32 call
+
+
+@torch.library.custom_op("bgan::blur2d_multi", mutates_args=(), device_types="cuda")
+def blur2d_multi(xs: Sequence[torch.Tensor], layout: int, rule: int, std_eff: float, radius: int) -> list[torch.Tensor]:
+    """[B x for x in xs] for 1 .. 4 equally shaped tensors: one launch for 128 x 128 planes."""
+    if not 1 <= len(xs) <= MAX_MULTI:
+        raise RuntimeError("blur2d_multi: 1 .. %d tensors per call, got %d" % (MAX_MULTI, len(xs)))
+    for x in xs:
+        _require_cuda(x, "blur2d_multi")
+        if x.shape != xs[0].shape or x.device != xs[0].device:
+            raise RuntimeError("blur2d_multi: tensors must share shape and device")
+    lib = _lib.load()
+    xs = [x.contiguous() for x in xs]
+    n, c, h, w = _dims(xs[0], layout)
+    ys = [torch.empty_like(x) for x in xs]
+    if xs[0].numel() == 0:
+        return ys
+    count = len(xs)
+    xp = (ctypes.c_void_p * count)(*[x.data_ptr() for x in xs])
+    yp = (ctypes.c_void_p * count)(*[y.data_ptr() for y in ys])
+    with _on_device(xs[0].device):
+        ws_bytes = lib.bgan_blur2d_workspace_bytes(n, c, h, w, layout, radius)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xs[0].device) if ws_bytes else None
+        rc = lib.bgan_blur2d_multi_f32(xp, yp, count, n, c, h, w, layout, rule, float(std_eff), radius, None,
+                                       ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr())
+    _lib.check(rc, "bgan_blur2d_multi_f32")
+    return ys
+
+
+@blur2d_multi.register_fake
+def _(xs, layout, rule, std_eff, radius):
+    return [torch.empty_like(x, memory_format=torch.contiguous_format) for x in xs]
+
+
+def _blur2d_multi_backward(ctx, grads):
+    # B is self-adjoint: the gradients of the outputs that have one go through the same (single) launch
+    live = [i for i, g in enumerate(grads) if g is not None]
+    out = [None] * len(grads)
+    if live:
+        for i, g in zip(live, blur2d_multi([grads[i] for i in live], ctx.layout, ctx.rule, ctx.std_eff, ctx.radius)):
+            out[i] = g
+    return out, None, None, None, None
+
+
+def _blur2d_multi_setup(ctx, inputs, output):
+    _, ctx.layout, ctx.rule, ctx.std_eff, ctx.radius = inputs
+
+
+blur2d_multi.register_autograd(_blur2d_multi_backward, setup_context=_blur2d_multi_setup)
+
+
+def lerp_rows(u: torch.Tensor, v: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """``u[i] + weights[i] * (v[i] - u[i])`` per leading index (no autograd: the gradient penalty detaches its interpolates,
+    reference wgan.py:237-241)."""
+    _require_cuda(u, "lerp_rows")
+    _require_cuda(v, "lerp_rows")
+    _require_cuda(weights, "lerp_rows(weights)")
+    if u.shape != v.shape or weights.numel() != u.shape[0]:
+        raise RuntimeError("lerp_rows: u and v must share a shape and weights must have one entry per leading index")
+    u, v, weights = u.detach().contiguous(), v.detach().contiguous(), weights.detach().contiguous()
+    out = torch.empty_like(u)
+    rows = u.shape[0]
+    if u.numel():
+        with _on_device(u.device):
+            rc = _lib.load().bgan_lerp_rows_f32(u.data_ptr(), v.data_ptr(), weights.data_ptr(), out.data_ptr(), rows, u.numel() // rows,
+                                                _stream_ptr())
+        _lib.check(rc, "bgan_lerp_rows_f32")
+    return out
 
 
 @torch.library.custom_op("bgan::blur2d_taps", mutates_args=(), device_types="cuda")

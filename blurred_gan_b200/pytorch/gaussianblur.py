@@ -94,3 +94,18 @@ class GaussianBlur(nn.Module):
         if k < 1:
             raise AssertionError("kernel size should be odd")
         return ops.blur2d(inputs, ops.LAYOUT_NCHW, ops.RULE_TORCH, self.std_value(), k // 2)
+
+    def forward_many(self, *inputs: torch.Tensor) -> list:
+        """``[self(x) for x in inputs]`` for 1 .. 4 equally shaped batches through one library call (one launch for
+        128 x 128 planes).  Not in the reference; serves a critic step that blurs real and generated batches with the
+        same sigma."""
+        for x in inputs:
+            if x.dim() != 4:
+                raise RuntimeError("GaussianBlur expects [N, C, H, W], got %s" % (tuple(x.shape),))
+            if not x.is_cuda:
+                raise RuntimeError("GaussianBlur (blurred_gan_b200) runs on CUDA tensors only; there is no CPU fallback")
+        self._image_size = min(inputs[0].shape[-2:])
+        k = self.kernel_size
+        if k < 1:
+            raise AssertionError("kernel size should be odd")
+        return list(ops.blur2d_multi(list(inputs), ops.LAYOUT_NCHW, ops.RULE_TORCH, self.std_value(), k // 2))

@@ -144,6 +144,10 @@ class WGAN(nn.Module):
         return self.discriminator(images)
 
     # ---- critic -------------------------------------------------------------------------------------
+    def _critic_scores(self, fakes, reals):
+        """``wgan.py:136-137``: scores of the generated, then of the real batch, dropout active."""
+        return self._scores(fakes, training=True), self._scores(reals, training=True)
+
     def discriminator_loss(self, reals, fakes, real_scores, fake_scores) -> torch.Tensor:
         return (fake_scores - real_scores).sum() * (1.0 / self.hparams.global_batch_size)  # wgan.py:128-130
 
@@ -151,8 +155,7 @@ class WGAN(nn.Module):
         """``wgan.py:132-151``."""
         with torch.no_grad():  # the tape only reaches the critic's variables: gradients w.r.t. the fakes are pruned
             fakes = self.generate_samples(training=False)
-        fake_scores = self._scores(fakes, training=True)
-        real_scores = self._scores(reals, training=True)
+        fake_scores, real_scores = self._critic_scores(fakes, reals)
         disc_loss = self.discriminator_loss(reals, fakes, real_scores, fake_scores)
         self.discriminator_optimizer.zero_grad(set_to_none=True)
         # like tape.gradient(loss, trainable_variables): only the paths that reach the critic's variables are
@@ -223,9 +226,12 @@ class WGANGP(WGAN):
         self.gp_term_metric = _Mean("gp_term")
         self.norm_term_metric = _Mean("norm_term")
 
+    def _gradient_penalty(self, reals, fakes) -> torch.Tensor:
+        return gradient_penalty(self.discriminator, reals, fakes)
+
     def discriminator_loss(self, reals, fakes, real_scores, fake_scores) -> torch.Tensor:
         disc_loss = super().discriminator_loss(reals, fakes, real_scores, fake_scores)
-        gp_term = self.hparams.gp_coefficient * gradient_penalty(self.discriminator, reals, fakes)
+        gp_term = self.hparams.gp_coefficient * self._gradient_penalty(reals, fakes)
         self.gp_term_metric(gp_term)
         disc_loss = disc_loss + gp_term
         # wgan.py:282-284: a [B] vector (norm over the last axis of [B, 1] scores) added to the scalar loss

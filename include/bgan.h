@@ -74,7 +74,23 @@ int bgan_blur2d_f32(const float* x_device, float* y_device, int n, int c, int he
                     int rule, float std_eff, int radius, const float* taps_device,
                     void* ws_device, size_t ws_bytes, void* stream);
 
-/* How the last bgan_blur2d_f32 call on this thread was executed: 1 = fused tile kernel with TMA
+/* The same blur applied to `count` (1 .. 4) equally shaped tensors: ys[t] = B xs[t].  xs / ys are HOST arrays of device
+ * pointers.  128 x 128 planes are served by ONE launch over all tensors (fuller persistent grid, one pipeline fill and
+ * drain instead of `count`); other shapes run one launch sequence per tensor on `stream`, sharing the scratch (size: the
+ * single-tensor query).  Call sites this serves: the critic step blurs the generated and the real batch with the same
+ * sigma back to back (wgan.py:136-137 through blurred_gan.py:30-35), SURVEY section 8f row N3.  No output may alias any
+ * other tensor of the call. */
+int bgan_blur2d_multi_f32(const float* const* xs_device, float* const* ys_device, int count, int n, int c, int height,
+                          int width, int layout, int rule, float std_eff, int radius, const float* taps_device,
+                          void* ws_device, size_t ws_bytes, void* stream);
+
+/* out[i][:] = u[i][:] + weights[i] * (v[i][:] - u[i][:]) for `rows` rows of `per_row` floats: the gradient-penalty
+ * interpolates x_hat = reals + a (fakes - reals) of wgan.py:237-239.  Applied to two *blurred* batches it yields
+ * B x_hat without a third forward blur (B is linear). */
+int bgan_lerp_rows_f32(const float* u_device, const float* v_device, const float* weights_device, float* out_device,
+                       int64_t rows, int64_t per_row, void* stream);
+
+/* How the last bgan_blur2d_f32 / bgan_blur2d_multi_f32 call on this thread was executed: 1 = fused tile kernel with TMA
  * staging, 2 = fused tile kernel with plain loads, 3 = two launches (row pass, column pass), 4 = tcgen05 tensor-core kernel (128 x 128 planes),
  * 5 = direct FFMA kernel for 128 x 128 images with radius <= 5 (NHWC: 4), 6 = two-pass tcgen05 kernel for planes of
  * 256 x 256 and more with radius 12 .. 256 (needs the workspace). */

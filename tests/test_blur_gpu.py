@@ -464,3 +464,115 @@ def test_randomised_kernel_selection_and_parity():
         seen.add(ops.last_blur_path())
         assert_close(got, bo.blur_images_tf_ref(xh, std), "tf rule NHWC std=%g" % std)
     assert {4, 5, 6} <= seen and (seen & {1, 2, 3}), seen
+
+
+# ---- several tensors per launch, interpolates between blurred batches -----------------------------------
+@pytest.mark.parametrize("std,rule", [(0.5, "torch"), (1.0, "torch"), (3.0, "torch"), (23.0, "torch"), (0.5, "tf"), (5.0, "tf")])
+@pytest.mark.parametrize("layout", ["NCHW", "NHWC"])
+@pytest.mark.parametrize("count,batch", [(2, 5), (3, 50), (4, 1)])
+def test_multi_tensor_launch_is_bitwise_the_single_launches(std, rule, layout, count, batch):
+    """One launch over `count` tensors (units numbered tensor after tensor; 3 x 50 x 3 = 450 planes makes CTAs cross tensor
+    boundaries) == `count` single launches, bit for bit (same kernels, same per-plane arithmetic)."""
+    from blurred_gan_b200 import ops
+
+    if rule == "torch" and layout == "NHWC":
+        pytest.skip("the torch-rule module is NCHW only")
+    shape = (batch, 3, 128, 128) if layout == "NCHW" else (batch, 128, 128, 3)
+    xs = [_dev(uniform_pm1(10 + t, shape)) * float(3 ** t) for t in range(count)]
+    lay = ops.LAYOUT_NCHW if layout == "NCHW" else ops.LAYOUT_NHWC
+    if rule == "torch":
+        _, r = bo.torch_rule_plan(std, 128, 128)
+        rl, s = ops.RULE_TORCH, std
+    else:
+        _, r, s = bo.tf_rule_plan(std, 128, 128)
+        rl = ops.RULE_TF
+    singles = []
+    for x in xs:
+        singles.append(ops.blur2d(x, lay, rl, float(s), r))
+        path_single = ops.last_blur_path()
+    multi = ops.blur2d_multi(xs, lay, rl, float(s), r)
+    assert ops.last_blur_path() == path_single and path_single in (4, 5)
+    assert len(multi) == count
+    for t in range(count):
+        assert torch.equal(multi[t], singles[t]), "tensor %d differs" % t
+
+
+def test_multi_tensor_other_shapes_modules_and_autograd():
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    # generic shapes: one launch sequence per tensor behind the same call
+    xs = [_dev(uniform_pm1(20 + t, (2, 3, 37, 50))) for t in range(3)]
+    mod = GaussianBlur(2.0).cuda()
+    for got, x in zip(mod.forward_many(*xs), xs):
+        assert torch.equal(got, mod(x))
+    layer = GaussianBlur2D(4.0).cuda()
+    big = [_dev(uniform_pm1(30 + t, (1, 3, 256, 256))) for t in range(2)]
+    for got, x in zip(layer.forward_many(*big), big):
+        assert torch.equal(got, layer(x))
+    # autograd through the multi op: backward and double backward are the same op on the gradients
+    a = _dev(uniform_pm1(40, (2, 3, 128, 128))).requires_grad_(True)
+    b = _dev(uniform_pm1(41, (2, 3, 128, 128))).requires_grad_(True)
+    ga, gb = _dev(uniform_pm1(42, (2, 3, 128, 128))), _dev(uniform_pm1(43, (2, 3, 128, 128)))
+    ya, yb = mod.forward_many(a, b)
+    da, db = torch.autograd.grad([ya, yb], [a, b], [ga, gb], create_graph=True)
+    assert torch.equal(da, mod(ga)) and torch.equal(db, mod(gb))
+    # the backward is differentiable again (double backward): d/dg <B g, v> = B v
+    va = _dev(uniform_pm1(44, (2, 3, 128, 128)))
+    gr = ga.clone().requires_grad_(True)
+    ya2, _ = mod.forward_many(a, b)
+    (d1,) = torch.autograd.grad(ya2, a, gr, create_graph=True)
+    (d2,) = torch.autograd.grad(d1, gr, va)
+    assert_close(d2, mod(va).cpu().numpy(), "double backward of the multi op")
+    # errors: too many tensors, mismatched shapes, CPU tensors
+    with pytest.raises(RuntimeError):
+        ops.blur2d_multi([a.detach()] * 5, ops.LAYOUT_NCHW, ops.RULE_TORCH, 2.0, 5)
+    with pytest.raises(RuntimeError):
+        ops.blur2d_multi([a.detach(), a.detach()[:1]], ops.LAYOUT_NCHW, ops.RULE_TORCH, 2.0, 5)
+    with pytest.raises(RuntimeError):
+        ops.blur2d_multi([a.detach().cpu()], ops.LAYOUT_NCHW, ops.RULE_TORCH, 2.0, 5)
+
+
+def test_multi_tensor_double_backward():
+    """Gradient-penalty pattern through the multi op: d/dx of ||B-adjoint grad||^2 equals the single-op result."""
+    from blurred_gan_b200 import ops
+
+    x = _dev(uniform_pm1(50, (2, 3, 128, 128)))
+    w = _dev(uniform_pm1(51, (2, 3, 128, 128)))
+
+    def penalty(blur_fn):
+        xa = x.clone().requires_grad_(True)
+        y = blur_fn(xa)
+        score = (y * y * w).sum()
+        (g,) = torch.autograd.grad(score, xa, create_graph=True)
+        (gg,) = torch.autograd.grad(g.square().sum(), xa)
+        return gg
+
+    single = penalty(lambda t: ops.blur2d(t, ops.LAYOUT_NCHW, ops.RULE_TORCH, 3.0, 7))
+    multi = penalty(lambda t: ops.blur2d_multi([t], ops.LAYOUT_NCHW, ops.RULE_TORCH, 3.0, 7)[0])
+    assert torch.equal(single, multi)
+
+
+@pytest.mark.parametrize("shape", [(7, 3, 128, 128), (5, 1, 28, 28), (3, 2, 5, 9), (0, 3, 8, 8)])
+def test_lerp_rows_is_the_reference_interpolation(shape):
+    """wgan.py:237-239: x_hat = reals + a * (fakes - reals), one weight per image; same fp32 expression, bit-exact or 1 ulp (FMA contraction)."""
+    from blurred_gan_b200 import ops
+
+    if shape[0]:
+        u, v = _dev(uniform_pm1(60, shape)), _dev(uniform_pm1(61, shape))
+    else:
+        u, v = torch.empty(shape, device="cuda"), torch.empty(shape, device="cuda")
+    a = torch.rand(shape[0], device="cuda")
+    got = ops.lerp_rows(u, v, a)
+    want = u.double() + a.double().view(-1, 1, 1, 1) * (v.double() - u.double())
+    assert got.shape == u.shape
+    if shape[0]:
+        assert (got.double() - want).abs().max().item() <= 2.5e-7
+        # linearity of the blur: B(lerp(x, z)) == lerp(B x, B z) to rounding -- what the fused critic step relies on
+        if shape[-1] >= 28:
+            r = 3
+            bl = lambda t: ops.blur2d(t, ops.LAYOUT_NCHW, ops.RULE_TORCH, 1.3, r)  # noqa: E731
+            lhs = bl(got)
+            rhs = ops.lerp_rows(bl(u), bl(v), a)
+            assert (lhs - rhs).abs().max().item() <= 1e-6

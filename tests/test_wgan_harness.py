@@ -102,6 +102,30 @@ def test_cfg1_mnist_step_on_cpu_issues_seven_blurs_and_anneals():
     assert gan.n_img == 192 and gan.n_batches == 3
 
 
+def test_fused_critic_step_equals_the_reference_step_with_six_blurs():
+    """one blur call for (fakes, reals) + interpolates taken between the blurred batches (the blur is
+    linear) + B applied to the critic-input gradient (B is self-adjoint) == the reference's critic step."""
+    results = []
+    for fused in (False, True):
+        blur = CountingBlur(2.5)
+        blur.applications = 0
+        torch.manual_seed(0)
+        hp = BlurredWGANGP.HyperParameters(batch_size=16, global_batch_size=16, initial_blur_std=2.5)
+        gan = BlurredWGANGP(nets.MnistGenerator(), nets.MnistDiscriminator(), hp, blur=blur, fused_critic=fused)
+        torch.manual_seed(1)
+        reals = torch.rand(16, 1, 28, 28) * 2 - 1
+        torch.manual_seed(2)
+        gan.train_on_batch(reals)
+        results.append((blur.applications, gan.metric_results(), [p.detach().clone() for p in gan.discriminator[1].parameters()]))
+    (n0, m0, p0), (n1, m1, p1) = results
+    assert (n0, n1) == (7, 6)  # critic: 2 fwd + B(grad) + its backward instead of 3 fwd + 1 bwd + 1 double-bwd
+    for k in m0:
+        assert m1[k] == pytest.approx(m0[k], rel=1e-4, abs=1e-6), k
+    for a, b in zip(p0, p1):
+        # an Adam step moves every weight by ~lr = 1e-3 in the direction of the gradient's sign: equal steps <=> equal gradients
+        assert (a - b).abs().max().item() <= 1e-4
+
+
 def test_drift_term_is_a_vector_like_the_reference():
     gan = _mnist_gan(OracleBlur2D(1.0), batch=8)
     reals = torch.rand(8, 1, 28, 28) * 2 - 1
@@ -196,3 +220,38 @@ def test_swd_metric_on_device_tensors():
             api.feed(mode, b[k])
         want = api.end(mode)
     assert res == pytest.approx(want, rel=1e-6)
+
+
+@pytest.mark.gpu
+def test_fused_critic_step_on_gpu(monkeypatch):
+    """Row N3 on the B200 path: forward_many (one launch for both batches) + lerp_rows between the blurred batches +
+    B on the critic-input gradient gives the unfused step's losses; 5 library blur calls per step instead of 7."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D
+
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    calls = {"single": 0, "multi": 0}
+    real_single, real_multi = ops.blur2d, ops.blur2d_multi
+    monkeypatch.setattr(ops, "blur2d", lambda *a, **k: (calls.__setitem__("single", calls["single"] + 1), real_single(*a, **k))[1])
+    monkeypatch.setattr(ops, "blur2d_multi", lambda *a, **k: (calls.__setitem__("multi", calls["multi"] + 1), real_multi(*a, **k))[1])
+    results = []
+    for fused in (False, True):
+        calls["single"] = calls["multi"] = 0
+        torch.manual_seed(0)
+        hp = BlurredWGANGP.HyperParameters(batch_size=8, global_batch_size=8, initial_blur_std=3.0)
+        gan = BlurredWGANGP(nets.CelebaGenerator(), nets.CelebaDiscriminator(), hp, blur=GaussianBlur2D(3.0), fused_critic=fused).cuda()
+        torch.manual_seed(1)
+        reals = torch.rand(8, 3, 128, 128, device="cuda") * 2 - 1
+        torch.manual_seed(2)
+        gan.train_on_batch(reals)
+        results.append((dict(calls), gan.metric_results(), [p.detach().clone() for p in gan.discriminator[1].parameters()]))
+    (c0, m0, p0), (c1, m1, p1) = results
+    # library blur calls per step, backward and double backward included (the ops' autograd formulas call the same ops)
+    assert c0 == {"single": 7, "multi": 0}
+    assert c1 == {"single": 4, "multi": 1}
+    for k in m0:
+        assert m1[k] == pytest.approx(m0[k], rel=2e-3, abs=1e-5), k
+    for a, b in zip(p0, p1):
+        assert (a - b).abs().max().item() <= 2e-3 * 1.01
+        assert ((a - b).abs() > 1e-4).float().mean().item() < 0.02
