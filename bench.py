@@ -382,6 +382,38 @@ def run_native(args, stds):
             nhwc.append({"std": s, "taps": 2 * radius + 1, "kernel": KERNELS.get(path, "path %d" % path).split(" ")[0], "launch_us": round(us, 2),
                          "hbm_frac": round(2 * plane_bytes / (us * 1e-6) / 1e9 / hbm_peak, 4)})
 
+    # ---- context: the critic step's pair of blurs (generated + real batch, same sigma) as ONE launch
+    multi = None
+    if world == 1 or rank == 0:
+        import ctypes
+
+        multi = []
+        for s in (5.0, 23.0):
+            _, radius, std_eff = _lib.blur_plan(_lib.RULE_TORCH, s, H, W)
+            pairs = [((ctypes.c_void_p * 2)(sets[(2 * i) % n_sets][0].data_ptr(), sets[(2 * i + 1) % n_sets][0].data_ptr()),
+                      (ctypes.c_void_p * 2)(sets[(2 * i) % n_sets][1].data_ptr(), sets[(2 * i + 1) % n_sets][1].data_ptr())) for i in range(n_sets)]
+            with torch.cuda.stream(stream):
+                sp = torch.cuda.current_stream().cuda_stream
+                res = {}
+                for name in ("two_launches", "one_launch"):
+                    def go(i):
+                        xp, yp = pairs[i % n_sets]
+                        if name == "one_launch":
+                            _lib.check(lib.bgan_blur2d_multi_f32(xp, yp, 2, BATCH, CH, H, W, 0, _lib.RULE_TORCH, std_eff, radius, None, None, 0, sp), "multi")
+                        else:
+                            for t in range(2):
+                                _lib.check(lib.bgan_blur2d_f32(xp[t], yp[t], BATCH, CH, H, W, 0, _lib.RULE_TORCH, std_eff, radius, None, None, 0, sp), "blur")
+
+                    go(0)
+                    c0.record(stream)
+                    for i in range(20):
+                        go(i + 1)
+                    c1.record(stream)
+                    stream.synchronize()
+                    res[name] = c0.elapsed_time(c1) / 20 * 1e3
+            multi.append({"std": s, "tensors": 2, "two_launches_us": round(res["two_launches"], 2), "one_launch_us": round(res["one_launch"], 2),
+                          "one_launch_hbm_frac": round(4 * plane_bytes / (res["one_launch"] * 1e-6) / 1e9 / hbm_peak, 4)})
+
     # ---- e2e through the public module with host buffers ----------------------------------------------
     e2e = None
     if True:
@@ -461,7 +493,7 @@ def run_native(args, stds):
                    "l2": "5 rotating buffer sets (1.0 GB per GPU) > 126 MB L2; one CUDA graph per step",
                    "parallelism": "batch sharded, %d x 256 images, no collective" % world},
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline, "per_std": per_std,
-        "copy_reference": copy_ref, "nhwc_tf_rule": nhwc,
+        "copy_reference": copy_ref, "nhwc_tf_rule": nhwc, "multi_tensor_launch": multi,
     }
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:

@@ -129,9 +129,93 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int mode, long 
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+// ---- cta_group::2: one dispatch drives the tensor cores of both SMs of a CTA pair (M = 256: 128 rows per SM; each CTA
+// supplies its own A rows and half of the N rows of B).  Only the leader CTA issues; the commit is multicast to both.
+__device__ __forceinline__ void mma2_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(a),
+                 "l"(b), "r"(id), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t id, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a),
+                 "l"(b), "r"(id), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma2_rate_kernel(int n, int mode, long long* cycles_out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t s_tmem;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    for (uint32_t i = threadIdx.x; i < kSmem / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[1])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    {
+        const uint32_t taddr = tmem + (static_cast<uint32_t>((threadIdx.x >> 5) * 32) << 16);
+        for (int c = 0; c < 128; c += 16) {
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr + c),
+                "r"(0)
+                : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // both CTAs: barriers initialised, TMEM allocated, operands zeroed
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (rank == 0 && threadIdx.x == 0) {
+        const uint32_t id = (1u << 4) | ((static_cast<uint32_t>(n) >> 3) << 17) | ((256u >> 4) << 24);  // M = 256
+        const uint32_t d = tmem + 128;
+        const uint64_t adesc = desc_sw128(smem_u32(smem)), bdesc = desc_sw128(smem_u32(smem) + 16384);
+        long long t0 = 0;
+        int batch = 0;
+        for (int rep = 0; rep < 2; ++rep) {
+            t0 = clock64();
+            for (int b = 0; b < kBatches; ++b, ++batch) {
+#pragma unroll
+                for (int k = 0; k < kPerBatch; ++k) {
+                    const uint64_t ks = static_cast<uint64_t>((k & 3) * 2);
+                    if (mode == 0)
+                        mma2_ss(d, adesc + ks, bdesc + ks, id, k > 0);
+                    else
+                        mma2_ts(d, tmem + 8 * (k & 7), bdesc + ks, id, k > 0);
+                }
+                asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                                 smem_u32(&bar[batch & 1])),
+                             "h"(static_cast<uint16_t>(3))
+                             : "memory");
+                if (b > 0) wait_bar(&bar[(batch - 1) & 1], ((batch - 1) >> 1) & 1);
+            }
+            wait_bar(&bar[(batch - 1) & 1], ((batch - 1) >> 1) & 1);
+        }
+        cycles_out[blockIdx.x >> 1] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // the partner CTA keeps its TMEM and barriers alive until the leader is done
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 }  // namespace
 
-int main() {
+int main(int argc, char** argv) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     long long* d_cycles = nullptr;
@@ -163,6 +247,27 @@ int main() {
             const double per = static_cast<double>(mx) / (kBatches * kPerBatch);
             printf("A from %s  N=%3d : %7.1f cycles per MMA (min SM %7.1f)   %6.1f cycles per 128x128x16 equivalent   kernel %.3f ms\n",
                    mode == 0 ? "smem" : "TMEM", n, per, static_cast<double>(mn) / (kBatches * kPerBatch), per * 128.0 / n, ms);
+        }
+    }
+    if (argc > 1 && atoi(argv[1]) == 2) {
+        const int pairs = sms / 2;
+        cudaFuncSetAttribute(mma2_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem));
+        printf("tcgen05.mma cta_group::2 kind::f16 M=256 (128 rows per SM) K=16, %d CTA pairs, %d MMAs per pair\n", pairs, kBatches * kPerBatch);
+        for (int mode = 0; mode < 2; ++mode) {
+            for (int n : {64, 128, 256}) {
+                mma2_rate_kernel<<<2 * pairs, 128, kSmem>>>(n, mode, d_cycles);
+                const cudaError_t err = cudaDeviceSynchronize();
+                if (err != cudaSuccess) {
+                    printf("cta_group::2 mode %d N %d: %s\n", mode, n, cudaGetErrorString(err));
+                    return 1;
+                }
+                cudaMemcpy(h, d_cycles, sizeof(long long) * pairs, cudaMemcpyDeviceToHost);
+                long long mx = 0;
+                for (int i = 0; i < pairs; ++i) mx = h[i] > mx ? h[i] : mx;
+                const double per = static_cast<double>(mx) / (kBatches * kPerBatch);
+                printf("A from %s  N=%3d : %7.1f cycles per dispatch = per SM and 128 x %d x 16 tile   (%6.1f per SM and 128x128x16 equivalent)\n",
+                       mode == 0 ? "smem" : "TMEM", n, per, n, per * 128.0 / n);
+            }
         }
     }
     return 0;
