@@ -32,6 +32,9 @@ SIGNATURES = {
     "bgan_pyr_up_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "bgan_swd_extract_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                      c_void_p, c_void_p]),
+    "bgan_swd_feed_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "bgan_swd_feed_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p),
+                                  c_void_p, c_size_t, c_void_p]),
     "bgan_swd_normalise_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_double, c_void_p]),
     "bgan_swd_project_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "bgan_swd_project_last_path": (c_int, []),

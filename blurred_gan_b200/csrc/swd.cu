@@ -25,21 +25,32 @@ __constant__ double kB5[5] = {1.0, 4.0, 6.0, 4.0, 1.0};
 // y[p, oy, ox] = sum_{dy,dx} B5[dy] B5[dx] / 256 * x[p, m(2 oy + dy - 2), m(2 ox + dx - 2)]
 // Every product and partial sum is exact in fp64 (weights are small integers / 256, inputs fp32),
 // so the result is the correctly rounded exact value -- bit-identical to scipy's fp64 accumulation.
-__global__ void pyr_down_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int oh, int ow) {
-    const int64_t total = static_cast<int64_t>(planes) * oh * ow;
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int ox = static_cast<int>(idx % ow);
-        const int oy = static_cast<int>((idx / ow) % oh);
-        const int p = static_cast<int>(idx / (static_cast<int64_t>(ow) * oh));
+// Index arithmetic is 32-bit (rows = planes * output height fits an int, checked by the launcher) and the border is
+// folded with compares when the image has >= 3 rows / columns (one reflection suffices for offsets in [-2, n + 1]); a
+// per-pixel 64-bit div / mod and the `%` of the general mirror made these two kernels ~3x slower than their loads.
+__device__ __forceinline__ int mirror101_near(int i, int n, bool small) {
+    if (small) return mirror101(i, n);
+    i = i < 0 ? -i : i;
+    return i < n ? i : 2 * (n - 1) - i;
+}
+
+__global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int oh,
+                                                       int ow) {
+    const unsigned total = static_cast<unsigned>(planes) * oh * ow;
+    const bool small = H < 3 || W < 3;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned r = idx / static_cast<unsigned>(ow);
+        const int ox = static_cast<int>(idx - r * ow);
+        const unsigned p = r / static_cast<unsigned>(oh);
+        const int oy = static_cast<int>(r - p * oh);
         const float* src = x + static_cast<size_t>(p) * H * W;
         int cols[5];
 #pragma unroll
-        for (int d = 0; d < 5; ++d) cols[d] = mirror101(2 * ox + d - 2, W);
+        for (int d = 0; d < 5; ++d) cols[d] = mirror101_near(2 * ox + d - 2, W, small);
         double acc = 0.0;
 #pragma unroll
         for (int dy = 0; dy < 5; ++dy) {
-            const float* row = src + static_cast<size_t>(mirror101(2 * oy + dy - 2, H)) * W;
+            const float* row = src + static_cast<size_t>(mirror101_near(2 * oy + dy - 2, H, small)) * W;
             double racc = 0.0;
 #pragma unroll
             for (int dx = 0; dx < 5; ++dx) racc += kB5[dx] * static_cast<double>(__ldg(row + cols[dx]));
@@ -51,32 +62,34 @@ __global__ void pyr_down_kernel(const float* __restrict__ x, float* __restrict__
 
 // y[p, Y, X] = (minuend ? minuend[p, Y, X] : 0) -/+ sum 4 B5 B5 / 256 * Z[m(Y+dy-2), m(X+dx-2)],
 // Z = x zero-stuffed to (2h, 2w): Z[2i, 2j] = x[i, j], zero elsewhere.
-__global__ void pyr_up_kernel(const float* __restrict__ x, const float* __restrict__ minuend, float* __restrict__ y, int planes,
-                              int h, int w) {
+__global__ void __launch_bounds__(256) pyr_up_kernel(const float* __restrict__ x, const float* __restrict__ minuend, float* __restrict__ y,
+                                                     int planes, int h, int w) {
     const int OH = 2 * h, OW = 2 * w;
-    const int64_t total = static_cast<int64_t>(planes) * OH * OW;
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int X = static_cast<int>(idx % OW);
-        const int Y = static_cast<int>((idx / OW) % OH);
-        const int p = static_cast<int>(idx / (static_cast<int64_t>(OW) * OH));
+    const unsigned total = static_cast<unsigned>(planes) * OH * OW;
+    const bool small = OH < 3 || OW < 3;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned r = idx / static_cast<unsigned>(OW);
+        const int X = static_cast<int>(idx - r * OW);
+        const unsigned p = r / static_cast<unsigned>(OH);
+        const int Y = static_cast<int>(r - p * OH);
         const float* src = x + static_cast<size_t>(p) * h * w;
+        int zx[5];
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) zx[dx] = mirror101_near(X + dx - 2, OW, small);
         double acc = 0.0;
 #pragma unroll
         for (int dy = 0; dy < 5; ++dy) {
-            const int zy = mirror101(Y + dy - 2, OH);
+            const int zy = mirror101_near(Y + dy - 2, OH, small);
             if (zy & 1) continue;
             const float* row = src + static_cast<size_t>(zy >> 1) * w;
             double racc = 0.0;
 #pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-                const int zx = mirror101(X + dx - 2, OW);
-                if (!(zx & 1)) racc += kB5[dx] * static_cast<double>(__ldg(row + (zx >> 1)));
-            }
+            for (int dx = 0; dx < 5; ++dx)
+                if (!(zx[dx] & 1)) racc += kB5[dx] * static_cast<double>(__ldg(row + (zx[dx] >> 1)));
             acc += kB5[dy] * racc;
         }
         const float up = static_cast<float>(acc * (4.0 / 256.0));
-        y[idx] = minuend ? (minuend[idx] - up) : up;
+        y[idx] = minuend ? (__ldg(minuend + idx) - up) : up;
     }
 }
 
@@ -246,6 +259,7 @@ extern "C" int bgan_pyr_down_f32(const float* x, float* y, int planes, int heigh
     BGAN_REQUIRE(x && y && planes > 0 && height > 0 && width > 0, BGAN_E_BADARG, "bgan_pyr_down_f32: bad arguments");
     const int oh = (height + 1) / 2, ow = (width + 1) / 2;
     const int64_t total = static_cast<int64_t>(planes) * oh * ow;
+    BGAN_REQUIRE(static_cast<int64_t>(planes) * height * width < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_pyr_down_f32: more than 2^31 pixels per call");
     pyr_down_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, planes, height, width, oh, ow);
     BGAN_LAUNCH_OK();
     return 0;
@@ -254,6 +268,7 @@ extern "C" int bgan_pyr_down_f32(const float* x, float* y, int planes, int heigh
 extern "C" int bgan_pyr_up_f32(const float* x, const float* minuend, float* y, int planes, int h, int w, void* stream) {
     BGAN_REQUIRE(x && y && planes > 0 && h > 0 && w > 0, BGAN_E_BADARG, "bgan_pyr_up_f32: bad arguments");
     const int64_t total = static_cast<int64_t>(planes) * 4 * h * w;
+    BGAN_REQUIRE(total < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_pyr_up_f32: more than 2^31 pixels per call");
     pyr_up_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, minuend, y, planes, h, w);
     BGAN_LAUNCH_OK();
     return 0;
@@ -271,6 +286,63 @@ extern "C" int bgan_swd_extract_f32(const float* level, int n, int c, int h, int
     extract_kernel<4><<<static_cast<unsigned>(ctas), 256, 0, static_cast<cudaStream_t>(stream)>>>(level, c, h, w, px, py, nhoods_per_image,
                                                                                               nhood, n_desc, desc_out, sums);
     BGAN_LAUNCH_OK();
+    return 0;
+}
+
+// One `feed` of sliced_wasserstein.API (sliced_wasserstein.py:119-123): Laplacian pyramid of the minibatch and the
+// descriptor gather of every level, as one host call (the same kernels as the three entry points above, launched back to
+// back on `stream`; per-minibatch host work is what bounds the feed phase of an evaluation).
+extern "C" size_t bgan_swd_feed_workspace_bytes(int n, int c, int h, int w, int levels) {
+    if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || levels < 1) return 0;
+    // level l < levels - 1: its residual (h_l x w_l); level l >= 1: its Gaussian image (h_l x w_l)
+    size_t floats = 0;
+    int hl = h, wl = w;
+    for (int l = 0; l < levels; ++l) {
+        const size_t plane = static_cast<size_t>(n) * c * hl * wl;
+        if (l < levels - 1) floats += plane;
+        if (l >= 1) floats += plane;
+        hl = (hl + 1) / 2;
+        wl = (wl + 1) / 2;
+    }
+    return floats * sizeof(float) + 256;
+}
+
+extern "C" int bgan_swd_feed_f32(const float* minibatch, int n, int c, int h, int w, int levels, const int32_t* positions,
+                                 int nhoods_per_image, int nhood, float* const* desc_out, double* const* sums, void* ws, size_t ws_bytes,
+                                 void* stream) {
+    BGAN_REQUIRE(minibatch && positions && desc_out && sums && levels >= 1 && levels <= 16, BGAN_E_BADARG, "bgan_swd_feed_f32: bad arguments");
+    BGAN_REQUIRE(levels == 1 || (ws && ws_bytes >= bgan_swd_feed_workspace_bytes(n, c, h, w, levels)), BGAN_E_WORKSPACE,
+                 "bgan_swd_feed_f32: workspace of %zu bytes required, got %zu", bgan_swd_feed_workspace_bytes(n, c, h, w, levels), ws_bytes);
+    for (int l = 0; l < levels; ++l) {
+        BGAN_REQUIRE((h >> l) > 0 && (w >> l) > 0 && ((h >> l) << l) == h && ((w >> l) << l) == w, BGAN_E_BADARG,
+                     "bgan_swd_feed_f32: %d x %d images do not halve %d times", h, w, levels - 1);
+        BGAN_REQUIRE(desc_out[l] && sums[l], BGAN_E_BADARG, "bgan_swd_feed_f32: null output for level %d", l);
+    }
+    const int64_t count = static_cast<int64_t>(n) * nhoods_per_image;
+    float* next = static_cast<float*>(ws);
+    const float* cur = minibatch;  // Gaussian image of the current level
+    int hl = h, wl = w;
+    for (int l = 0; l < levels; ++l) {
+        const int32_t* px = positions + static_cast<int64_t>(2 * l) * count;
+        const int32_t* py = px + count;
+        const float* level = cur;
+        if (l < levels - 1) {
+            const size_t plane = static_cast<size_t>(n) * c * hl * wl;
+            float* resid = next;
+            float* coarse = next + plane;
+            next = coarse + plane / 4;
+            int rc = bgan_pyr_down_f32(cur, coarse, n * c, hl, wl, stream);                       // :85-86
+            if (rc) return rc;
+            rc = bgan_pyr_up_f32(coarse, cur, resid, n * c, hl / 2, wl / 2, stream);              // :87  residual = g - pyr_up(down)
+            if (rc) return rc;
+            level = resid;
+            cur = coarse;
+        }
+        const int rc = bgan_swd_extract_f32(level, n, c, hl, wl, px, py, nhoods_per_image, nhood, desc_out[l], sums[l], stream);  // :13-23
+        if (rc) return rc;
+        hl /= 2;
+        wl /= 2;
+    }
     return 0;
 }
 

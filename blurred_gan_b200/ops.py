@@ -283,6 +283,39 @@ def swd_extract(level: torch.Tensor, px, py, nhoods_per_image: int, nhood: int, 
     return out
 
 
+def swd_feed(minibatch: torch.Tensor, positions: torch.Tensor, levels: int, nhoods_per_image: int, nhood: int, sums: list,
+             scratch: dict | None = None) -> list:
+    """One ``API.feed``: Laplacian pyramid + descriptor gather of every level through ONE library call.
+
+    ``positions``: int32 CUDA tensor [levels][x | y][n * nhoods_per_image]; ``sums``: per level an fp64 CUDA tensor (>= 2C
+    entries) that the channel statistics are accumulated into; ``scratch``: dict keeping the pyramid workspace between
+    calls.  Returns the per-level descriptor tensors [n * nhoods_per_image, C, nhood, nhood]."""
+    _require_cuda(minibatch, "swd_feed")
+    minibatch = minibatch.contiguous()
+    n, c, h, w = minibatch.shape
+    dev = minibatch.device
+    count = n * nhoods_per_image
+    assert positions.is_cuda and positions.dtype == torch.int32 and positions.is_contiguous() and positions.numel() == 2 * levels * count
+    assert len(sums) == levels and all(t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() >= 2 * c for t in sums)
+    lib = _lib.load()
+    ws_bytes = lib.bgan_swd_feed_workspace_bytes(n, c, h, w, levels)
+    ws = scratch.get("feed_ws") if scratch is not None else None
+    if ws is None or ws.numel() < ws_bytes or ws.device != dev:
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if scratch is not None:
+            scratch["feed_ws"] = ws
+    outs = [torch.empty((count, c, nhood, nhood), dtype=torch.float32, device=dev) for _ in range(levels)]
+    out_p = (ctypes.c_void_p * levels)(*[t.data_ptr() for t in outs])
+    sum_p = (ctypes.c_void_p * levels)(*[t.data_ptr() for t in sums])
+    with _on_device(dev):
+        rc = lib.bgan_swd_feed_f32(minibatch.data_ptr(), n, c, h, w, levels, positions.data_ptr(), nhoods_per_image, nhood, out_p, sum_p,
+                                   ws.data_ptr(), ws_bytes, _stream_ptr())
+    _lib.check(rc, "bgan_swd_feed_f32")
+    if scratch is None:
+        ws.record_stream(torch.cuda.current_stream(dev))
+    return outs
+
+
 def swd_normalise_(desc: torch.Tensor, sums: torch.Tensor, count: float) -> torch.Tensor:
     """In place (desc - mean_c) / std_c for desc [rows, C, a, b]; mean/std derived on device from ``sums``."""
     _require_cuda(desc, "swd_normalise_")

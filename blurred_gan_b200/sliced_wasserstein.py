@@ -202,6 +202,7 @@ class API:
         self.group = group
         self.rank, self.world = _dist.world_info(group) if (distributed or group is not None) else (0, 1)
         self._stage = None
+        self._scratch = {}  # pyramid workspace of feed(), reused between minibatches
         # one pyramid level per power of two down to 16 px (image_shape = (C, H, W); H drives it, like the reference)
         self.resolutions = []
         size = image_shape[1]
@@ -225,18 +226,30 @@ class API:
         mb = _to_device(minibatch, self.device)
         n, c = mb.shape[0], mb.shape[1]
         assert mb.dim() == 4 and c == 3
-        levels = generate_laplacian_pyramid(mb, len(self.resolutions))
+        n_levels = len(self.resolutions)
+        h, w = mb.shape[2], mb.shape[3]
+        sizes = [(h >> lod, w >> lod) for lod in range(n_levels)]
+        fused = h % (1 << (n_levels - 1)) == 0 and w % (1 << (n_levels - 1)) == 0  # (odd sizes: level-by-level calls below)
         if self._sums is None:
-            self._sums = [torch.zeros(2 * c + 1, dtype=torch.float64, device=mb.device) for _ in levels]
+            self._sums = [torch.zeros(2 * c + 1, dtype=torch.float64, device=mb.device) for _ in range(n_levels)]
+        levels = None if fused else generate_laplacian_pyramid(mb, n_levels)
+        if levels is not None:
+            sizes = [(lv.shape[2], lv.shape[3]) for lv in levels]
         # All draws of this feed, in the reference's order (finest level first; x then y), written straight into a pinned
         # staging buffer and uploaded asynchronously.
         count = n * self.nhoods_per_image
         if self._stage is None:
             self._stage = _PinnedRing()
-        slot, host = self._stage.take(2 * len(levels) * count)
-        _dist.positions_packed_for_round(n, [(lv.shape[2], lv.shape[3]) for lv in levels], self.nhood_size, self.nhoods_per_image,
-                                         self.rank, self.world, out=host.numpy())
+        slot, host = self._stage.take(2 * n_levels * count)
+        _dist.positions_packed_for_round(n, sizes, self.nhood_size, self.nhoods_per_image, self.rank, self.world, out=host.numpy())
         packed = self._stage.upload(slot, host, mb.device)
+        if fused:
+            # pyramid + gather of all levels: one library call (11 launches back to back), the pyramid lives in a reused workspace
+            descs = ops.swd_feed(mb, packed, n_levels, self.nhoods_per_image, self.nhood_size, self._sums, self._scratch)
+            for lod, d in enumerate(descs):
+                self.descriptors[lod].append(d)
+                self._rows[lod] += count
+            return
         for lod, level in enumerate(levels):
             px = packed[2 * lod * count : (2 * lod + 1) * count]
             py = packed[(2 * lod + 1) * count : (2 * lod + 2) * count]

@@ -119,6 +119,17 @@ int bgan_swd_extract_f32(const float* level_device, int n, int c, int h, int w, 
                          const int32_t* py_device, int nhoods_per_image, int nhood, float* desc_out_device,
                          double* sums_device, void* stream);
 
+/* sliced_wasserstein.py:119-123  one API.feed as ONE host call: Laplacian pyramid of the minibatch [n, c, h, w] (h, w
+ * divisible by 2^(levels-1)) and the descriptor gather of every level -- the kernels of bgan_pyr_down_f32,
+ * bgan_pyr_up_f32 (residual form) and bgan_swd_extract_f32 launched back to back on `stream`; the minibatch is not
+ * modified.  positions_device: int32 [levels][x | y][n * nhoods_per_image] (the layout bgan_swd_positions_i32 writes);
+ * desc_out / sums: HOST arrays of `levels` device pointers (per level: [n * nhoods_per_image, c, nhood, nhood] floats;
+ * 2c doubles accumulated into, as in bgan_swd_extract_f32).  Scratch: bgan_swd_feed_workspace_bytes. */
+size_t bgan_swd_feed_workspace_bytes(int n, int c, int h, int w, int levels);
+int bgan_swd_feed_f32(const float* minibatch_device, int n, int c, int h, int w, int levels, const int32_t* positions_device,
+                      int nhoods_per_image, int nhood, float* const* desc_out_device, double* const* sums_device,
+                      void* ws_device, size_t ws_bytes, void* stream);
+
 /* sliced_wasserstein.py:31-32  desc = (desc - mean_c) / std_c in place, with mean/std derived on
  * the device from sums_device (as filled by bgan_swd_extract_f32, possibly all-reduced across
  * ranks) and `count` = number of values per channel.  rows x (C*per_channel) floats. */

@@ -260,3 +260,36 @@ def test_distributed_api_two_ranks_match_single_process(tmp_path):
     want = _run_api(so.API((3, 64, 64)), reals, fakes, 4)  # single process, same global minibatch order
     np.testing.assert_array_equal(got[0][0], want[0])
     np.testing.assert_allclose(got[0][1], want[1], rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(6, 3, 128, 128), (3, 3, 64, 96), (2, 3, 16, 16), (4, 3, 20, 28)])
+def test_fused_feed_is_bitwise_the_level_by_level_feed(shape):
+    """bgan_swd_feed_f32 (pyramid + gather of all levels in one call) == the level-by-level calls: descriptors and channel
+    statistics bit for bit, same position stream.  20 x 28 has one level only."""
+    from blurred_gan_b200 import sliced_wasserstein as sw
+
+    x = _dev(uniform_pm1(77, shape))
+    results = []
+    for fused in (True, False):
+        np.random.seed(5)
+        api = sw.API(shape[1:])
+        api.begin("reals")
+        if not fused:
+            # the reference's own call sequence (sliced_wasserstein.py:121-123): pyramid, then per level x and y draws + gather
+            levels = sw.generate_laplacian_pyramid(x, len(api.resolutions))
+            sums = [torch.zeros(7, dtype=torch.float64, device="cuda") for _ in levels]
+            descs = [sw.get_descriptors_for_minibatch(lv, 7, 128, s[:6]) for lv, s in zip(levels, sums)]
+        else:
+            api.feed("reals", x)
+            descs = [d[0] for d in api.descriptors]
+            sums = api._sums
+        results.append(([d.clone() for d in descs], [s[:6].clone() for s in sums], np.random.get_state()[2]))
+    (d0, s0, p0), (d1, s1, p1) = results
+    assert p0 == p1, "the two paths consumed different numbers of draws"
+    assert len(d0) == len(d1)
+    for a, b in zip(d0, d1):
+        assert a.shape == b.shape and torch.equal(a, b)
+    for a, b in zip(s0, s1):
+        # fp64 atomics: the accumulation order inside extract_kernel is not deterministic
+        assert torch.allclose(a, b, rtol=1e-12, atol=1e-9)
+    assert torch.equal(x, _dev(uniform_pm1(77, shape))), "feed must not modify its input"
