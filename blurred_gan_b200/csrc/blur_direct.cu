@@ -55,20 +55,22 @@ struct DirectCfg {
     __host__ __device__ static constexpr size_t smem_bytes(int r) { return stages(r) * stage_bytes(r) + 1024; }
 };
 
+template <int NT>
 struct DirectArgs {
-    float* y[kMaxMulti];  // one output per tensor of a multi-tensor launch (bgan_blur2d_multi_f32)
+    float* y[NT];  // one output per tensor of a multi-tensor launch (bgan_blur2d_multi_f32)
     const float* taps_dev;
     int units;             // all tensors together: planes (NCHW) or 2 * images (NHWC), tensor after tensor
     int units_per_tensor;
     int rule;
     float std_eff;
 };
+template <int NT>
 struct DirectMaps {
-    CUtensorMap m[kMaxMulti];
+    CUtensorMap m[NT];
 };
 
-template <int ES, int R>
-__global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const DirectArgs a, const __grid_constant__ DirectMaps maps) {
+template <int ES, int R, int NT>
+__global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const DirectArgs<NT> a, const __grid_constant__ DirectMaps<NT> maps) {
     using C = DirectCfg<ES>;
     constexpr int kTaps = 2 * R + 1;
     constexpr int kLaneFloats = 4 * ES;      // floats of one row owned by a lane (4 pixels)
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
         // of back-to-back launches.
         for (int it = 0; it < n_it && it < kStages; ++it) {
             int unit = first + it * stride;
-            const CUtensorMap* tmap = &maps.m[multi_locate(unit, a.units_per_tensor)];
+            const CUtensorMap* tmap = &maps.m[multi_locate<NT>(unit, a.units_per_tensor)];
             const int image = unit / C::kUnitsPerImage, row0 = (unit % C::kUnitsPerImage) * C::kUnitRows - R;
 #pragma unroll
             for (int p = 0; p < C::kPanels; ++p) tma_prefetch_l2_3d(tmap, p * C::kPanelFloats - kPad, row0, image);
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
                 const int b = it % kStages, use = it / kStages;
                 if (use > 0) mbar_wait(empty + b, (use - 1) & 1);
                 int unit = first + it * stride;
-                const CUtensorMap* tmap = &maps.m[multi_locate(unit, a.units_per_tensor)];
+                const CUtensorMap* tmap = &maps.m[multi_locate<NT>(unit, a.units_per_tensor)];
                 const int image = unit / C::kUnitsPerImage, row0 = (unit % C::kUnitsPerImage) * C::kUnitRows - R;
                 unsigned char* dst = smem + b * C::stage_bytes(R);
                 mbar_arrive_expect_tx(full + b, static_cast<uint32_t>(C::box_rows(R) * kPitch * C::kPanels * sizeof(float)));
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kDirectThreads, 1) blur_direct128_kernel(const
     for (int it = group; it < n_it; it += C::kGroups) {
         const int b = it % kStages, use = it / kStages;
         int unit = first + it * stride;
-        float* const y = multi_pick(a.y, multi_locate(unit, a.units_per_tensor));
+        float* const y = multi_pick<NT>(a.y, multi_locate<NT>(unit, a.units_per_tensor));
         const int image = unit / C::kUnitsPerImage, out_row0 = (unit % C::kUnitsPerImage) * C::kUnitRows + gwarp * C::kRowsPerWarp;
         mbar_wait(full + b, use & 1);
         const float* src = reinterpret_cast<const float*>(smem + b * C::stage_bytes(R)) + lane_off + gwarp * C::kRowsPerWarp * kPitch;
@@ -222,10 +224,10 @@ EncodeTiledFn direct_encode_fn() {
     return fn;
 }
 
-template <int ES, int R>
-int launch_direct(const MultiIO& io, int images, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
+template <int ES, int R, int NT>
+int launch_direct_nt(const MultiIO& io, int images, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
     using C = DirectCfg<ES>;
-    DirectMaps maps;
+    DirectMaps<NT> maps;
     memset(&maps, 0, sizeof(maps));
     thread_local bool bound = false;  // cuTensorMapEncodeTiled needs a context bound to the calling thread
     if (!bound) {
@@ -243,7 +245,7 @@ int launch_direct(const MultiIO& io, int images, int rule, float std_eff, const 
                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);  // out-of-bounds rows read as zeros
         BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(res));
     }
-    auto kernel = blur_direct128_kernel<ES, R>;
+    auto kernel = blur_direct128_kernel<ES, R, NT>;
     thread_local int attr_dev = -1;
     int dev = 0;
     BGAN_CUDA_OK(cudaGetDevice(&dev));
@@ -252,7 +254,13 @@ int launch_direct(const MultiIO& io, int images, int rule, float std_eff, const 
         attr_dev = dev;
     }
     const int per_tensor = images * C::kUnitsPerImage, units = per_tensor * io.count;
-    DirectArgs a{{io.y[0], io.y[1], io.y[2], io.y[3]}, taps_dev, units, per_tensor, rule, std_eff};
+    DirectArgs<NT> a;
+    for (int t = 0; t < NT; ++t) a.y[t] = t < io.count ? io.y[t] : nullptr;
+    a.taps_dev = taps_dev;
+    a.units = units;
+    a.units_per_tensor = per_tensor;
+    a.rule = rule;
+    a.std_eff = std_eff;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(static_cast<unsigned>(std::min(units, device_sm_count())));
@@ -267,6 +275,12 @@ int launch_direct(const MultiIO& io, int images, int rule, float std_eff, const 
     cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
     BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, a, maps));
     return 0;
+}
+
+template <int ES, int R>
+int launch_direct(const MultiIO& io, int images, int rule, float std_eff, const float* taps_dev, cudaStream_t stream) {
+    return io.count == 1 ? launch_direct_nt<ES, R, 1>(io, images, rule, std_eff, taps_dev, stream)
+                         : launch_direct_nt<ES, R, kMaxMulti>(io, images, rule, std_eff, taps_dev, stream);
 }
 
 template <int ES>

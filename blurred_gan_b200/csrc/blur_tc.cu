@@ -65,14 +65,16 @@ constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) <<
 // named barriers: X(i) tiles ready (even / odd plane), compute-warp internal, Z(i) ready (4 + i % 2)
 constexpr int kBarA0 = 1, kBarFetch = 2, kBarA1 = 3, kBarB0 = 4;
 
+template <int NT>
 struct TcMaps {
-    CUtensorMap m[kMaxMulti];
+    CUtensorMap m[NT];
 };
 
+template <int NT>
 struct TcArgs {
     long long* trace;  // debug: clock64 stamps of CTA 0 (nullptr in production), see tools/trace_tc.py
-    const float* x[kMaxMulti];  // only read directly for es > 1 (es == 1 goes through the tensor maps)
-    float* y[kMaxMulti];        // one (x, y) pair per tensor of a multi-tensor launch (bgan_blur2d_multi_f32)
+    const float* x[NT];  // only read directly for es > 1 (es == 1 goes through the tensor maps)
+    float* y[NT];        // one (x, y) pair per tensor of a multi-tensor launch (bgan_blur2d_multi_f32)
     int es;  // 1: planes are contiguous [128][128]; 3: NHWC, plane p = channel p % 3 of image p / 3 (interleaved floats)
     int planes;             // all tensors together, numbered tensor after tensor
     int planes_per_tensor;
@@ -225,7 +227,8 @@ __device__ __forceinline__ void gather_plane_load(unsigned char* stage, const fl
 //
 // The tensor pipe never waits for the split (it works on the next plane's GEMM1 meanwhile) and the compute warps never
 // hold the next plane in registers across the split.  Operand conventions: see the top of the file.
-__global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs a, const __grid_constant__ TcMaps maps) {
+template <int NT>
+__global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs<NT> a, const __grid_constant__ TcMaps<NT> maps) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
     float* s_g = reinterpret_cast<float*>(smem + kOffMisc);
@@ -266,10 +269,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             // is where the previous grid's stores land, so it can never expose stale data -- but it takes the DRAM latency
             // (~2.8 us when all CTAs ask at once) out of the pipeline fill of back-to-back launches.
             int p0 = static_cast<int>(blockIdx.x), p1 = static_cast<int>(blockIdx.x + gridDim.x);
-            const CUtensorMap* m0 = &maps.m[multi_locate(p0, a.planes_per_tensor)];
+            const CUtensorMap* m0 = &maps.m[multi_locate<NT>(p0, a.planes_per_tensor)];
             tma_prefetch_l2_3d(m0, 0, 0, p0);
             if (blockIdx.x + gridDim.x < static_cast<unsigned>(a.planes)) {
-                const CUtensorMap* m1 = &maps.m[multi_locate(p1, a.planes_per_tensor)];
+                const CUtensorMap* m1 = &maps.m[multi_locate<NT>(p1, a.planes_per_tensor)];
                 tma_prefetch_l2_3d(m1, 0, 0, p1);
             }
             asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     if (a.es != 1 && warp < kTcWarps) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         int p0 = static_cast<int>(blockIdx.x);
-        const float* x0 = multi_pick(a.x, multi_locate(p0, a.planes_per_tensor));
+        const float* x0 = multi_pick<NT>(a.x, multi_locate<NT>(p0, a.planes_per_tensor));
         gather_plane_load(smem + kOffStage, x0, mbar_tma, p0, a.es, tid);
     }
     stamp();  // taps
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         const int c0 = ((warp - kStoreWarp0) >> 2) * 64;  // first D2 column (= output row h') of this warp
         for (int i = 0; i < n; ++i) {
             int p = first + i * stride;
-            float* const y = multi_pick(a.y, multi_locate(p, a.planes_per_tensor));
+            float* const y = multi_pick<NT>(a.y, multi_locate<NT>(p, a.planes_per_tensor));
             mbar_wait(mbar_g2, i & 1);
             tc_fence_after();
             if (warp == kStoreWarp0) stamp_role(256);  // G2(i) complete
@@ -447,15 +450,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             if (a.es != 1) {
                 if (next_plane < a.planes) {
                     int pn = next_plane;
-                    const float* xn = multi_pick(a.x, multi_locate(pn, a.planes_per_tensor));
+                    const float* xn = multi_pick<NT>(a.x, multi_locate<NT>(pn, a.planes_per_tensor));
                     gather_plane_load(smem + kOffStage, xn, mbar_tma, pn, a.es, tid);
                 }
             } else if (tid == 0 && next_plane < a.planes) {
                 int pn = next_plane, pa = next_plane + stride;
                 mbar_arrive_expect_tx(mbar_tma, kP * kP * 4);
-                tma_load_3d(smem + kOffStage, &maps.m[multi_locate(pn, a.planes_per_tensor)], mbar_tma, 0, 0, pn);
+                tma_load_3d(smem + kOffStage, &maps.m[multi_locate<NT>(pn, a.planes_per_tensor)], mbar_tma, 0, 0, pn);
                 if (next_plane + stride < a.planes)  // warm L2 one more ahead
-                    tma_prefetch_l2_3d(&maps.m[multi_locate(pa, a.planes_per_tensor)], 0, 0, pa);
+                    tma_prefetch_l2_3d(&maps.m[multi_locate<NT>(pa, a.planes_per_tensor)], 0, 0, pa);
             }
         };
         auto convert = [&](int buf, int it_of_plane) {
@@ -584,8 +587,9 @@ bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, c
 
 // `planes` counts geometry planes: N*C for NCHW (es = 1), N images of 128 x 384 interleaved floats for NHWC (es = 3)
 // (per tensor; io.count equally shaped tensors are blurred by one launch)
-int blur_tc_launch(const MultiIO& io, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
-    TcMaps maps;
+template <int NT>
+int blur_tc_launch_nt(const MultiIO& io, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
+    TcMaps<NT> maps;
     memset(&maps, 0, sizeof(maps));
     bind_primary_context();
     // the tensor map is only used for es == 1; for NHWC it describes the same memory as dense 128-float rows (never loaded)
@@ -604,15 +608,23 @@ int blur_tc_launch(const MultiIO& io, int planes, int es, int rule, float std_ef
     int dev = 0;
     BGAN_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
         attr_dev = dev;
     }
     const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
     const int per_tensor = planes * es, units = per_tensor * io.count;  // 128 x 128 channel planes
-    TcArgs a{tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr,
-             {io.x[0], io.x[1], io.x[2], io.x[3]},
-             {io.y[0], io.y[1], io.y[2], io.y[3]},
-             es, units, per_tensor, rule, std_eff, radius};
+    TcArgs<NT> a;
+    a.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr;
+    for (int t = 0; t < NT; ++t) {
+        a.x[t] = t < io.count ? io.x[t] : nullptr;
+        a.y[t] = t < io.count ? io.y[t] : nullptr;
+    }
+    a.es = es;
+    a.planes = units;
+    a.planes_per_tensor = per_tensor;
+    a.rule = rule;
+    a.std_eff = std_eff;
+    a.radius = radius;
     // balanced persistent grid: every CTA runs the same number of rounds (768 planes on 148 SMs -> 128 CTAs x 6 planes
     // rather than 28 CTAs x 6 + 120 x 5), so that the HBM-bound steady state has no latency-bound tail round
     const int sms = device_sm_count();
@@ -634,8 +646,14 @@ int blur_tc_launch(const MultiIO& io, int planes, int es, int rule, float std_ef
     const char* no_pdl = getenv("BGAN_BLUR_NO_PDL");
     cfg.attrs = attr;
     cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
-    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel, a, maps));
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<NT>, a, maps));
     return 0;
+}
+
+// (per tensor; io.count equally shaped tensors are blurred by one launch)
+int blur_tc_launch(const MultiIO& io, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
+    return io.count == 1 ? blur_tc_launch_nt<1>(io, planes, es, rule, std_eff, radius, stream)
+                         : blur_tc_launch_nt<kMaxMulti>(io, planes, es, rule, std_eff, radius, stream);
 }
 
 }  // namespace bgan

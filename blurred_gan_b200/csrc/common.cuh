@@ -68,11 +68,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// unit -> (tensor, unit inside the tensor) for a multi-tensor launch; `per` units per tensor, at most kMaxMulti tensors
+// unit -> (tensor, unit inside the tensor) for a launch over NT tensors; `per` units per tensor.  NT = 1 (the single-tensor
+// entry point) folds to nothing: the kernels are instantiated for NT = 1 and NT = kMaxMulti so that the hot single-tensor
+// launch carries neither the extra tensor maps nor the selects (measured: 0.1 - 0.2 us per launch).
+template <int NT>
 __device__ __forceinline__ int multi_locate(int& unit, int per) {
     int t = 0;
 #pragma unroll
-    for (int k = 1; k < kMaxMulti; ++k) {
+    for (int k = 1; k < NT; ++k) {
         if (unit >= per) {
             unit -= per;
             ++t;
@@ -81,9 +84,13 @@ __device__ __forceinline__ int multi_locate(int& unit, int per) {
     return t;
 }
 // p[t] of a kernel-parameter array without dynamic indexing (which would copy the array to local memory)
-template <typename T>
-__device__ __forceinline__ T multi_pick(T const (&p)[kMaxMulti], int t) {
-    return t == 0 ? p[0] : t == 1 ? p[1] : t == 2 ? p[2] : p[3];
+template <int NT, typename T>
+__device__ __forceinline__ T multi_pick(T const (&p)[NT], int t) {
+    static_assert(NT == 1 || NT == kMaxMulti, "instantiated for one tensor or for kMaxMulti");
+    if constexpr (NT == 1)
+        return p[0];
+    else
+        return t == 0 ? p[0] : t == 1 ? p[1] : t == 2 ? p[2] : p[3];
 }
 
 // mbarrier + TMA (cp.async.bulk.tensor) primitives, written as the PTX they are.
