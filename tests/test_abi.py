@@ -75,3 +75,37 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     plane = 2 * 3 * 1024 * 1024 * 4
     assert plane <= lib.bgan_blur2d_workspace_bytes(2, 3, 1024, 1024, 0, 160) <= plane + 2 * 3 * 2048 * 4 + 512
     assert lib.bgan_blur2d_workspace_bytes(2, 3, 1024, 1024, 1, 160) == plane                     # NHWC: two launches of the tile kernel
+
+
+def test_new_entry_points_validate_their_arguments_without_a_gpu(lib):
+    """bgan_blur2d_multi_f32 / bgan_lerp_rows_f32 / bgan_swd_feed_f32: argument errors are reported before any CUDA call."""
+    two = (ctypes.c_void_p * 2)(256, 512)
+    outs = (ctypes.c_void_p * 2)(1024, 2048)
+    five_x = (ctypes.c_void_p * 5)(*range(256, 256 * 6, 256))
+    five_y = (ctypes.c_void_p * 5)(*range(4096, 4096 + 256 * 5, 256))
+    assert lib.bgan_blur2d_multi_f32(None, None, 2, 1, 3, 128, 128, 0, 0, 1.0, 1, None, None, 0, None) < 0
+    assert lib.bgan_blur2d_multi_f32(five_x, five_y, 5, 1, 3, 128, 128, 0, 0, 1.0, 1, None, None, 0, None) < 0   # at most 4 tensors
+    assert b"tensors" in lib.bgan_last_error()
+    assert lib.bgan_blur2d_multi_f32(two, outs, 0, 1, 3, 128, 128, 0, 0, 1.0, 1, None, None, 0, None) < 0
+    aliased = (ctypes.c_void_p * 2)(1024, 256)                                                               # ys[1] == xs[0]
+    assert lib.bgan_blur2d_multi_f32(two, aliased, 2, 1, 3, 128, 128, 0, 0, 1.0, 1, None, None, 0, None) < 0
+    assert b"aliases" in lib.bgan_last_error()
+    same_out = (ctypes.c_void_p * 2)(1024, 1024)
+    assert lib.bgan_blur2d_multi_f32(two, same_out, 2, 1, 3, 128, 128, 0, 0, 1.0, 1, None, None, 0, None) < 0
+    assert lib.bgan_blur2d_multi_f32(two, outs, 2, 1, 3, 128, 128, 0, 0, -1.0, 1, None, None, 0, None) < 0      # std must be positive
+    assert lib.bgan_blur2d_multi_f32(two, outs, 2, 1, 2, 128, 128, _lib.LAYOUT_NHWC, 0, 1.0, 1, None, None, 0, None) < 0
+
+    assert lib.bgan_lerp_rows_f32(None, None, None, None, 4, 16, None) < 0
+    assert lib.bgan_lerp_rows_f32(256, 512, 768, 1024, 4, 0, None) < 0
+    assert lib.bgan_lerp_rows_f32(256, 512, 768, 1024, 0, 16, None) == 0                                        # empty batch: nothing to do
+
+    # pyramid workspace of one feed: residuals of levels 0..L-2 and Gaussian images of levels 1..L-1
+    n, c = 64, 3
+    want = 4 * n * c * (128 * 128 + 64 * 64 + 32 * 32 + 64 * 64 + 32 * 32 + 16 * 16)
+    assert want <= lib.bgan_swd_feed_workspace_bytes(n, c, 128, 128, 4) <= want + 512
+    assert lib.bgan_swd_feed_workspace_bytes(n, c, 128, 128, 0) == 0
+    assert lib.bgan_swd_feed_f32(None, n, c, 128, 128, 4, None, 128, 7, None, None, None, 0, None) < 0
+    four = (ctypes.c_void_p * 4)(256, 512, 768, 1024)
+    assert lib.bgan_swd_feed_f32(256, n, c, 128, 128, 4, 512, 128, 7, four, four, None, 0, None) < 0            # workspace missing
+    assert b"workspace" in lib.bgan_last_error()
+    assert lib.bgan_swd_feed_f32(256, n, c, 100, 100, 4, 512, 128, 7, four, four, 2048, 1 << 30, None) < 0      # 100 does not halve 3 times
