@@ -17,6 +17,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libbgan_b200.so")
 SOURCES = ["capi.cu", "blur.cu", "blur_tc.cu", "blur_direct.cu", "blur_axis.cu", "swd.cu", "project_tc.cu", "sort.cu", "hostrng.cu"]
+# host-only sources compiled by g++ (name -> extra flags); selected at run time by a CPU feature check in hostrng.cu
+CPP_SOURCES = {"hostrng_avx2.cpp": ["-mavx2"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -60,8 +62,20 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(res.stderr)
         return obj
 
+    def compile_cpp(src: str) -> str:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src.replace(".cpp", ".o"))
+        if force or _stale(obj, [path]):
+            gxx = shutil.which("g++") or "g++"
+            cmd = [gxx, "-O3", "-std=c++17", "-fPIC", *CPP_SOURCES[src], "-c", path, "-o", obj]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("g++ failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))
+        return obj
+
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
+    objs += [compile_cpp(src) for src in CPP_SOURCES]
     if force or _stale(LIB_PATH, objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-o", LIB_PATH, *objs]
         res = subprocess.run(cmd, capture_output=True, text=True)

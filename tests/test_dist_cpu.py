@@ -195,3 +195,39 @@ def test_packed_positions_equal_the_numpy_draws(world, rank):
         np.random.seed(7)
         again = bd.positions_packed_for_round(5, sizes, 7, 128, rank, world)
     assert np.array_equal(again, got)
+
+
+def test_mt19937_scalar_and_avx2_paths_agree(tmp_path):
+    """The replay has a scalar body and an AVX2 body (csrc/hostrng_avx2.cpp, chosen at run time): same draws, same final
+    state.  The choice is latched at the first call, so the scalar body runs in a child process (BGAN_RNG_SCALAR=1)."""
+    import subprocess
+    import sys
+
+    script = r"""
+import ctypes, sys, numpy as np
+sys.path.insert(0, %r)
+from blurred_gan_b200 import _lib
+lib = _lib.load()
+st = np.random.RandomState(7).get_state()
+key, pos = np.array(st[1], dtype=np.uint32, copy=True), ctypes.c_int(int(st[2]))
+acc = []
+for low, high, count, store in [(3, 125, 65536, True), (3, 61, 4099, False), (3, 29, 7, True), (3, 13, 8, True), (0, 1 << 31, 1000, True),
+                                (3, 125, 623, False), (3, 125, 625, True), (-9, 1000003, 31337, True)]:
+    out = np.full(count, -1, dtype=np.int32)
+    assert lib.bgan_mt19937_randint_i32(key.ctypes.data, ctypes.byref(pos), low, high, count, out.ctypes.data if store else None) == 0
+    acc.append(out)
+np.savez(sys.argv[1], key=key, pos=pos.value, **{"o%%d" %% i: a for i, a in enumerate(acc)})
+""" % ROOT
+    results = []
+    for scalar in ("0", "1"):
+        path = str(tmp_path / ("rng%s.npz" % scalar))
+        env = dict(os.environ, BGAN_RNG_SCALAR=scalar)
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=120)
+        results.append(np.load(path))
+    a, b = results
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k
+    # and both are numpy's draws
+    rs = np.random.RandomState(7)
+    assert np.array_equal(a["o0"], rs.randint(3, 125, size=65536))
