@@ -284,12 +284,13 @@ def swd_extract(level: torch.Tensor, px, py, nhoods_per_image: int, nhood: int, 
 
 
 def swd_feed(minibatch: torch.Tensor, positions: torch.Tensor, levels: int, nhoods_per_image: int, nhood: int, sums: list,
-             scratch: dict | None = None) -> list:
+             scratch: dict | None = None, outs: list | None = None) -> list:
     """One ``API.feed``: Laplacian pyramid + descriptor gather of every level through ONE library call.
 
     ``positions``: int32 CUDA tensor [levels][x | y][n * nhoods_per_image]; ``sums``: per level an fp64 CUDA tensor (>= 2C
     entries) that the channel statistics are accumulated into; ``scratch``: dict keeping the pyramid workspace between
-    calls.  Returns the per-level descriptor tensors [n * nhoods_per_image, C, nhood, nhood]."""
+    calls; ``outs``: optional per-level destinations (contiguous [n * nhoods_per_image, C, nhood, nhood] views, e.g. slices of a
+    growing per-level array).  Returns the per-level descriptor tensors [n * nhoods_per_image, C, nhood, nhood]."""
     _require_cuda(minibatch, "swd_feed")
     minibatch = minibatch.contiguous()
     n, c, h, w = minibatch.shape
@@ -304,7 +305,11 @@ def swd_feed(minibatch: torch.Tensor, positions: torch.Tensor, levels: int, nhoo
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         if scratch is not None:
             scratch["feed_ws"] = ws
-    outs = [torch.empty((count, c, nhood, nhood), dtype=torch.float32, device=dev) for _ in range(levels)]
+    if outs is None:
+        outs = [torch.empty((count, c, nhood, nhood), dtype=torch.float32, device=dev) for _ in range(levels)]
+    else:
+        assert len(outs) == levels and all(t.shape == (count, c, nhood, nhood) and t.dtype == torch.float32 and t.is_contiguous() and
+                                           t.device == dev for t in outs)
     out_p = (ctypes.c_void_p * levels)(*[t.data_ptr() for t in outs])
     sum_p = (ctypes.c_void_p * levels)(*[t.data_ptr() for t in sums])
     with _on_device(dev):

@@ -281,7 +281,8 @@ def test_fused_feed_is_bitwise_the_level_by_level_feed(shape):
             descs = [sw.get_descriptors_for_minibatch(lv, 7, 128, s[:6]) for lv, s in zip(levels, sums)]
         else:
             api.feed("reals", x)
-            descs = [d[0] for d in api.descriptors]
+            descs = [slab[: api._rows[lod]] for lod, slab in enumerate(api._slabs)]
+            assert all(not chunks for chunks in api.descriptors)
             sums = api._sums
         results.append(([d.clone() for d in descs], [s[:6].clone() for s in sums], np.random.get_state()[2]))
     (d0, s0, p0), (d1, s1, p1) = results
