@@ -85,3 +85,75 @@ def test_swd_surface():
     with pytest.raises(AssertionError):
         api.begin("bogus")
     np.testing.assert_array_equal(swd.gaussian_filter * 256, np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1]))
+
+
+def test_api_feed_bookkeeping_with_the_library_stubbed_out(monkeypatch):
+    """Host logic of ``API.feed`` / ``end`` on the fused path -- the per-level arrays that grow geometrically and are filled
+    in place, the row accounting, the position stream -- with the library calls replaced by CPU stubs (the arithmetic itself
+    is covered by the GPU parity tests).  Ragged last minibatch, capacity doublings, slack trimming at ``end``."""
+    from blurred_gan_b200 import dist as bd
+    from blurred_gan_b200 import ops
+
+    calls = []
+
+    def fake_feed(minibatch, positions, levels, per_image, nhood, sums, scratch=None, outs=None):
+        n = minibatch.shape[0]
+        assert outs is not None and len(outs) == levels and positions.numel() == 2 * levels * n * per_image
+        for lod, o in enumerate(outs):
+            assert o.shape == (n * per_image, 3, nhood, nhood) and o.is_contiguous()
+            o.fill_(float(len(calls) * 10 + lod))  # minibatch index and level, recoverable from the array
+            sums[lod][:6] += 1.0
+        calls.append(n)
+        return outs
+
+    class Ring:
+        def take(self, n):
+            return 0, torch.empty(n, dtype=torch.int32)
+
+        def upload(self, k, host, device):
+            return host
+
+    monkeypatch.setattr(swd, "_to_device", lambda a, device=None: torch.as_tensor(a, dtype=torch.float32))
+    monkeypatch.setattr(swd, "_PinnedRing", Ring)
+    monkeypatch.setattr(ops, "swd_feed", fake_feed)
+    monkeypatch.setattr(ops, "swd_normalise_", lambda desc, sums, count: desc)
+    api = swd.API((3, 64, 64))
+    assert api.resolutions == [64, 32, 16]
+    np.random.seed(3)
+    state0 = np.random.get_state()[1].copy()
+    api.begin("reals")
+    sizes = [2, 2, 2, 2, 2, 2, 2, 2, 2, 1]  # 19 images: capacity 4 -> 8 -> 16 minibatches of 2, ragged tail
+    for n in sizes:
+        api.feed("reals", np.zeros((n, 3, 64, 64), np.float32))
+    assert calls == sizes
+    rows = sum(sizes) * 128
+    assert api._rows == [rows] * 3 and all(s.shape[0] >= rows for s in api._slabs)
+    assert all(not c for c in api.descriptors)
+    for lod, slab in enumerate(api._slabs):
+        got = slab[:rows, 0, 0, 0].reshape(-1).numpy()
+        want = np.concatenate([np.full(n * 128, i * 10 + lod, np.float32) for i, n in enumerate(sizes)])
+        assert np.array_equal(got, want)  # every minibatch landed behind the previous one, growth copied the old rows
+    assert not np.array_equal(np.random.get_state()[1], state0)  # positions came from numpy's global stream
+    # reference stream: 10 feeds x 3 levels x (x, y) randint draws
+    np.random.seed(3)
+    for n in sizes:
+        for size in (64, 32, 16):
+            np.random.randint(3, size - 3, size=(n * 128, 1, 1, 1))
+            np.random.randint(3, size - 3, size=(n * 128, 1, 1, 1))
+    expect_after = np.random.get_state()
+    np.random.seed(3)
+    bd_state = np.random.get_state()
+    np.random.set_state(bd_state)
+    api2 = swd.API((3, 64, 64))
+    api2.begin("reals")
+    calls.clear()
+    for n in sizes:
+        api2.feed("reals", np.zeros((n, 3, 64, 64), np.float32))
+    got_after = np.random.get_state()
+    assert np.array_equal(got_after[1], expect_after[1]) and got_after[2] == expect_after[2]
+    monkeypatch.setattr(bd, "all_reduce_sum_", lambda t, group=None: t)
+    res = api2.end("reals")
+    assert res == [0.0, 0.0, 0.0, 0.0] and api2._slabs is None
+    assert all(d.shape == (rows, 147) for d in api2.desc_real)
+    # 19 of 32 minibatch slots used: the kept set was trimmed to its own storage
+    assert all(d.untyped_storage().nbytes() == rows * 147 * 4 for d in api2.desc_real)
