@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libbgan_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RULE_TORCH, RULE_TF, RULE_EXPLICIT = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1

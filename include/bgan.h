@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BGAN_ABI_VERSION 1
+#define BGAN_ABI_VERSION 2 /* 2: + bgan_blur2d_multi_f32, bgan_lerp_rows_f32, bgan_swd_feed_f32 (+ workspace query) */
 
 /* tap rules */
 #define BGAN_RULE_TORCH 0    /* pytorch/gaussianblur.py:9-14 (normaliser inside the exp)  */
