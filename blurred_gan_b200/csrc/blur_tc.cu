@@ -62,7 +62,6 @@ constexpr uint32_t kSmemTc = kOffMisc + 1024 /* taps */ + 256;
 constexpr float kLoScale = 2048.0f;
 // instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t kIdesc256 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // N = 256
 // named barriers: X(i) tiles ready (even / odd plane), compute-warp internal, Z(i) ready (4 + i % 2)
 constexpr int kBarA0 = 1, kBarFetch = 2, kBarA1 = 3, kBarB0 = 4;
 
@@ -116,44 +115,6 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
             "}\n" ::"r"(d_tmem),
             "r"(a_tmem), "l"(bdesc), "r"(kIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-            : "memory");
-    }
-}
-// The "stacked" variant (template flag ST; selected with BGAN_TC_STACKED=1 until it has replaced the default) spends fewer
-// tensor-pipe cycles per plane: on this pool a dispatch costs ~105 cycles for every N <= 128 and 140 for N = 256
-// (tools/mma_rate.cu), so GEMM2 runs  [D2a | D2b] = Z_hi x [T_hi | T_lo']  as ONE N = 256 stream (the T tiles are stored
-// with the lo' rows behind the hi rows of every K-block) plus  D2a += Z_lo x T_hi,  16 dispatches instead of 24, and the
-// store warps write (D2a + 2^-11 D2b) / scale.  D2 then needs 256 TMEM columns, which T gives up: GEMM1 takes A = T from
-// the same shared-memory tiles (SS mode).
-__device__ __forceinline__ void mma_ts_n(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-        : "memory");
-}
-// D (+)= A B with both operands from shared memory; scale_d11: D = A B + D * 2^-11
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, bool scale_d11) {
-    if (scale_d11) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p, 11;\n\t"
-            "}\n" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-            "}\n" ::"r"(d_tmem),
-            "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
             : "memory");
     }
 }
@@ -235,32 +196,6 @@ __device__ __forceinline__ void issue_g2(uint32_t d_tmem, uint32_t dz, uint32_t 
     for (int k = 0; k < 8; ++k) mma_ts(d_tmem, dz + 32 * (k >> 1) + 8 * (k & 1) + 16, dh + kstep(k), 1, false);
 }
 
-// ---- stacked variant ----
-// T tiles with the lo' rows behind the hi rows: K-block kb at kb * 32 KB, inside it `half` (0 = hi, 1 = lo') at half * 16 KB
-__device__ __forceinline__ uint32_t t_tile_off_stacked(int half, int row, int k) {
-    return (k >> 6) * (2 * kKBlockBytes) + half * kKBlockBytes + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
-}
-__device__ __forceinline__ constexpr uint64_t kstep_t(int k) { return static_cast<uint64_t>((k >> 2) * ((2 * kKBlockBytes) >> 4) + (k & 3) * 2); }
-// GEMM1, SS mode: A = T hi / lo' halves of the stacked tiles at `t_tiles`, B = X hi / lo tiles
-__device__ __forceinline__ void issue_g1_ss(uint32_t d_tmem, uint32_t t_tiles, uint32_t x_hi, uint32_t x_lo) {
-    const uint64_t th = smem_desc(t_tiles), tl = smem_desc(t_tiles + kKBlockBytes), dh = smem_desc(x_hi), dl = smem_desc(x_lo);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mma_ss(d_tmem, tl + kstep_t(k), dh + kstep(k), k > 0, false);
-    mma_ss(d_tmem, th, dh, 1, true);
-#pragma unroll
-    for (int k = 1; k < 8; ++k) mma_ss(d_tmem, th + kstep_t(k), dh + kstep(k), 1, false);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mma_ss(d_tmem, th + kstep_t(k), dl + kstep(k), 1, false);
-}
-// GEMM2: [D2a | D2b] = Z_hi x [T_hi | T_lo'] (N = 256, columns d_tmem .. d_tmem + 255), then D2a += Z_lo x T_hi (N = 128)
-__device__ __forceinline__ void issue_g2_stacked(uint32_t d_tmem, uint32_t dz, uint32_t t_tiles) {
-    const uint64_t dt = smem_desc(t_tiles);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mma_ts_n(d_tmem, dz + 32 * (k >> 1) + 8 * (k & 1), dt + kstep_t(k), kIdesc256, k > 0);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mma_ts_n(d_tmem, dz + 32 * (k >> 1) + 8 * (k & 1) + 16, dt + kstep_t(k), kIdesc, 1);
-}
-
 // NHWC (es == 3): TMA cannot walk the innermost dimension with an element stride (elementStrides[0] is ignored for
 // non-interleaved maps) and the channel stride of 12 bytes is not a legal tensor-map stride either, so the compute
 // threads gather channel c of image n with 4-byte cp.async (LDGSTS) straight into the same row-major [128][128] staging
@@ -292,7 +227,7 @@ __device__ __forceinline__ void gather_plane_load(unsigned char* stage, const fl
 //
 // The tensor pipe never waits for the split (it works on the next plane's GEMM1 meanwhile) and the compute warps never
 // hold the next plane in registers across the split.  Operand conventions: see the top of the file.
-template <int NT, bool ST>
+template <int NT>
 __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs<NT> a, const __grid_constant__ TcMaps<NT> maps) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const float* stage = reinterpret_cast<const float*>(smem + kOffStage);
@@ -383,7 +318,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     }
     __syncthreads();
     stamp();  // chunk table
-    if (!ST && warp < kTcWarps) {  // T hi | lo' -> TMEM: lane = row w', 32-bit column = two consecutive K (= w) elements
+    if (warp < kTcWarps) {  // T hi | lo' -> TMEM: lane = row w', 32-bit column = two consecutive K (= w) elements
         tc_fence_after();
         const uint32_t t_tmem = *s_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + (warp >> 2) * 16;
         const int trow = (warp & 3) * 32 + lane;
@@ -404,10 +339,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
         const int row = idx & 127, chunk = idx >> 7;
         const int i = chunk * 8 - row + a.radius + 7;
         const bool band = i >= 0 && i < n_taps + 7;
-        const uint32_t off_hi = ST ? t_tile_off_stacked(0, row, chunk * 8) : tile_off(row, chunk * 8);
-        const uint32_t off_lo = ST ? t_tile_off_stacked(1, row, chunk * 8) : kTileBytes + tile_off(row, chunk * 8);
-        *reinterpret_cast<uint4*>(smem + kOffT1 + off_hi) = band ? s_chi[i] : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(smem + kOffT1 + off_lo) = band ? s_clo[i] : make_uint4(0, 0, 0, 0);
+        const uint32_t off = tile_off(row, chunk * 8);
+        *reinterpret_cast<uint4*>(smem + kOffT1 + off) = band ? s_chi[i] : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(smem + kOffT2 + off) = band ? s_clo[i] : make_uint4(0, 0, 0, 0);
     }
     stamp();  // T in TMEM and in shared memory
     fence_proxy_async();
@@ -415,8 +349,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    // TMEM columns: T [0, 128) | D1 even | D1 odd | D2 [384, 512);   stacked: D1 even [0, 128) | D1 odd | D2a [256, 384) | D2b [384, 512)
-    const uint32_t tT = tmem, dz = ST ? tmem : tmem + 128, d2 = ST ? tmem + 256 : tmem + 384;
+    const uint32_t tT = tmem, dz = tmem + 128, d2 = tmem + 384;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int row = (warp & 3) * 32 + lane;
     const int first = blockIdx.x, stride = gridDim.x;
@@ -431,10 +364,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             if (lane == 0) {
                 tc_fence_after();
                 stamp_role(128);
-                if constexpr (ST)
-                    issue_g1_ss(dz, sbase + kOffT1, sbase + kOffO1, sbase + kOffO2);
-                else
-                    issue_g1(dz, tT, sbase + kOffO1, sbase + kOffO2);
+                issue_g1(dz, tT, sbase + kOffO1, sbase + kOffO2);
                 umma_commit(mbar_g1);
                 stamp_role(128);
             }
@@ -446,10 +376,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
                 if (lane == 0) {
                     tc_fence_after();
                     stamp_role(128);  // G1 issue starts
-                    if constexpr (ST)
-                        issue_g1_ss(dz + ((i + 1) & 1) * 128, sbase + kOffT1, sbase + kOffO1, sbase + kOffO2);
-                    else
-                        issue_g1(dz + ((i + 1) & 1) * 128, tT, sbase + kOffO1, sbase + kOffO2);
+                    issue_g1(dz + ((i + 1) & 1) * 128, tT, sbase + kOffO1, sbase + kOffO2);
                     umma_commit(mbar_g1 + ((i + 1) & 1));
                     stamp_role(128);  // G1 issued
                 }
@@ -460,10 +387,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
                 if (i >= 1) mbar_wait(mbar_d2free, (i - 1) & 1);  // D2(i - 1) is in the store warps' registers
                 tc_fence_after();
                 stamp_role(128);  // G2 issue starts
-                if constexpr (ST)
-                    issue_g2_stacked(d2, dz + (i & 1) * 128, sbase + kOffT1);
-                else
-                    issue_g2(d2, dz + (i & 1) * 128, sbase + kOffT1, sbase + kOffT2);
+                issue_g2(d2, dz + (i & 1) * 128, sbase + kOffT1, sbase + kOffT2);
                 umma_commit(mbar_g2);
                 stamp_role(128);  // G2 issued
             }
@@ -482,30 +406,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) blur_tc128_kernel(const TcArgs
             float* q = y + (static_cast<size_t>(p / a.es) * kP * kP + row) * a.es + p % a.es;
             const size_t ld = static_cast<size_t>(kP) * a.es;  // floats between consecutive output rows h'
             q += static_cast<size_t>(c0) * ld;
-            if constexpr (ST) {
-                // D2 = D2a + 2^-11 D2b, 32 output rows at a time; D2 is released once the second half is in registers (the
-                // tensor pipe runs GEMM1 of the plane after next in between, so that is early enough)
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float va[32], vb[32];
-                    tmem_ld32_nowait(d2 + lane_base + c0 + 32 * half, va);
-                    tmem_ld32_nowait(d2 + 128 + lane_base + c0 + 32 * half, vb);
-                    tmem_ld_wait(va);
-                    tmem_ld_wait(vb);
-                    if (half == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(mbar_d2free);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j, q += ld) {
-                        asm volatile("" : "+l"(q));
-                        __stcs(q, fmaf(vb[j], 1.0f / kLoScale, va[j]) * inv);
-                    }
-                }
-                if (warp == kStoreWarp0) stamp_role(256);  // stores of plane i issued
-                continue;
-            }
             float o0[32], o1[32];
             tmem_ld32_nowait(d2 + lane_base + c0, o0);
             tmem_ld32_nowait(d2 + lane_base + c0 + 32, o1);
@@ -687,7 +587,7 @@ bool blur_tc_eligible(int planes, int H, int Wc, int ES, int radius, int rule, c
 
 // `planes` counts geometry planes: N*C for NCHW (es = 1), N images of 128 x 384 interleaved floats for NHWC (es = 3)
 // (per tensor; io.count equally shaped tensors are blurred by one launch)
-template <int NT, bool ST>
+template <int NT>
 int blur_tc_launch_nt(const MultiIO& io, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
     TcMaps<NT> maps;
     memset(&maps, 0, sizeof(maps));
@@ -708,7 +608,7 @@ int blur_tc_launch_nt(const MultiIO& io, int planes, int es, int rule, float std
     int dev = 0;
     BGAN_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<NT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_tc128_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTc)));
         attr_dev = dev;
     }
     const char* tr = getenv("BGAN_TC_TRACE_PTR");  // debug only: device pointer (decimal) to 128 int64
@@ -746,22 +646,14 @@ int blur_tc_launch_nt(const MultiIO& io, int planes, int es, int rule, float std
     const char* no_pdl = getenv("BGAN_BLUR_NO_PDL");
     cfg.attrs = attr;
     cfg.numAttrs = (no_pdl && atoi(no_pdl)) ? 0 : 1;
-    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<NT, ST>, a, maps));
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_tc128_kernel<NT>, a, maps));
     return 0;
 }
 
 // (per tensor; io.count equally shaped tensors are blurred by one launch)
 int blur_tc_launch(const MultiIO& io, int planes, int es, int rule, float std_eff, int radius, cudaStream_t stream) {
-    // the stacked-GEMM2 variant (see mma_ts_n above) is opt-in until it has been validated as the default
-    static const bool stacked = [] {
-        const char* e = getenv("BGAN_TC_STACKED");
-        return e && atoi(e) != 0;
-    }();
-    if (stacked)
-        return io.count == 1 ? blur_tc_launch_nt<1, true>(io, planes, es, rule, std_eff, radius, stream)
-                             : blur_tc_launch_nt<kMaxMulti, true>(io, planes, es, rule, std_eff, radius, stream);
-    return io.count == 1 ? blur_tc_launch_nt<1, false>(io, planes, es, rule, std_eff, radius, stream)
-                         : blur_tc_launch_nt<kMaxMulti, false>(io, planes, es, rule, std_eff, radius, stream);
+    return io.count == 1 ? blur_tc_launch_nt<1>(io, planes, es, rule, std_eff, radius, stream)
+                         : blur_tc_launch_nt<kMaxMulti>(io, planes, es, rule, std_eff, radius, stream);
 }
 
 }  // namespace bgan
