@@ -157,3 +157,21 @@ def test_api_feed_bookkeeping_with_the_library_stubbed_out(monkeypatch):
     assert all(d.shape == (rows, 147) for d in api2.desc_real)
     # 19 of 32 minibatch slots used: the kept set was trimmed to its own storage
     assert all(d.untyped_storage().nbytes() == rows * 147 * 4 for d in api2.desc_real)
+
+
+def test_multi_tensor_entry_points_refuse_cpu_tensors_and_bad_lists():
+    """forward_many / blur_images_many / lerp_rows keep the no-CPU-fallback rule of the single-tensor calls."""
+    from blurred_gan_b200 import ops
+
+    x = torch.zeros(2, 3, 16, 16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        tblur.GaussianBlur(1.0).forward_many(x, x.clone())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        tfblur.GaussianBlur2D(1.0).forward_many(x, x.clone())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        tfblur.blur_images_many([x], 1.0)
+    with pytest.raises(RuntimeError, match="4-D"):
+        tfblur.blur_images_many([x[0]], 1.0)
+    with pytest.raises(RuntimeError):
+        ops.lerp_rows(x, x, torch.zeros(2))
+    assert ops.MAX_MULTI == 4
