@@ -17,6 +17,9 @@ namespace bgan {
 // hostrng_avx2.cpp (g++ -mavx2): the same draws, eight MT19937 words at a time
 bool cpu_has_avx2();
 void randint_fill_avx2(uint32_t* key, int* pos_inout, uint32_t mask, uint32_t bound, int32_t lo32, int64_t count, int32_t* out);
+// hostrng_avx512.cpp (g++ -mavx512f): sixteen words at a time
+bool cpu_has_avx512f();
+void randint_fill_avx512(uint32_t* key, int* pos_inout, uint32_t mask, uint32_t bound, int32_t lo32, int64_t count, int32_t* out);
 }  // namespace bgan
 
 namespace {
@@ -64,7 +67,14 @@ bool randint_fill(uint32_t* key, int* pos_inout, int64_t low, int64_t high, int6
     mask |= mask >> 16;
     const uint32_t bound = static_cast<uint32_t>(rng);
     const int32_t lo32 = static_cast<int32_t>(low);
-    static const bool use_avx2 = bgan::cpu_has_avx2() && !(getenv("BGAN_RNG_SCALAR") && atoi(getenv("BGAN_RNG_SCALAR")));
+    // widest body the CPU (and the OS) supports; BGAN_RNG_SCALAR=1 / BGAN_RNG_NO_AVX512=1 pin a narrower one (tests)
+    static const bool scalar_only = getenv("BGAN_RNG_SCALAR") && atoi(getenv("BGAN_RNG_SCALAR"));
+    static const bool use_avx512 = !scalar_only && bgan::cpu_has_avx512f() && !(getenv("BGAN_RNG_NO_AVX512") && atoi(getenv("BGAN_RNG_NO_AVX512")));
+    static const bool use_avx2 = !scalar_only && bgan::cpu_has_avx2();
+    if (use_avx512) {
+        bgan::randint_fill_avx512(key, pos_inout, mask, bound, lo32, count, out);
+        return true;
+    }
     if (use_avx2) {
         bgan::randint_fill_avx2(key, pos_inout, mask, bound, lo32, count, out);
         return true;

@@ -197,9 +197,10 @@ def test_packed_positions_equal_the_numpy_draws(world, rank):
     assert np.array_equal(again, got)
 
 
-def test_mt19937_scalar_and_avx2_paths_agree(tmp_path):
-    """The replay has a scalar body and an AVX2 body (csrc/hostrng_avx2.cpp, chosen at run time): same draws, same final
-    state.  The choice is latched at the first call, so the scalar body runs in a child process (BGAN_RNG_SCALAR=1)."""
+def test_mt19937_scalar_avx2_and_avx512_paths_agree(tmp_path):
+    """The replay has a scalar body, an AVX2 body and an AVX-512 body (csrc/hostrng_avx2.cpp, hostrng_avx512.cpp; the widest
+    one the CPU supports is chosen at run time): same draws, same final state.  The choice is latched at the first call, so
+    each body runs in its own child process (BGAN_RNG_SCALAR=1 / BGAN_RNG_NO_AVX512=1 pin the narrower ones)."""
     import subprocess
     import sys
 
@@ -219,15 +220,17 @@ for low, high, count, store in [(3, 125, 65536, True), (3, 61, 4099, False), (3,
 np.savez(sys.argv[1], key=key, pos=pos.value, **{"o%%d" %% i: a for i, a in enumerate(acc)})
 """ % ROOT
     results = []
-    for scalar in ("0", "1"):
-        path = str(tmp_path / ("rng%s.npz" % scalar))
-        env = dict(os.environ, BGAN_RNG_SCALAR=scalar)
+    for i, pins in enumerate(({}, {"BGAN_RNG_NO_AVX512": "1"}, {"BGAN_RNG_SCALAR": "1"})):
+        path = str(tmp_path / ("rng%d.npz" % i))
+        env = {k: v for k, v in os.environ.items() if not k.startswith("BGAN_RNG_")}
+        env.update(pins)
         subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=120)
         results.append(np.load(path))
-    a, b = results
-    assert sorted(a.files) == sorted(b.files)
-    for k in a.files:
-        assert np.array_equal(a[k], b[k]), k
+    a = results[0]
+    for b in results[1:]:
+        assert sorted(a.files) == sorted(b.files)
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), k
     # and both are numpy's draws
     rs = np.random.RandomState(7)
     assert np.array_equal(a["o0"], rs.randint(3, 125, size=65536))
