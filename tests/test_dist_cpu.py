@@ -234,3 +234,72 @@ np.savez(sys.argv[1], key=key, pos=pos.value, **{"o%%d" %% i: a for i, a in enum
     # and both are numpy's draws
     rs = np.random.RandomState(7)
     assert np.array_equal(a["o0"], rs.randint(3, 125, size=65536))
+
+
+# ---- data-parallel train step (BASELINE configs[2]): gradients all-reduced over gloo == the single-process step -----------
+def _tiny_gan(blur):
+    """A blurred WGAN with deterministic linear nets (no dropout / batch norm), so that a sharded step must reproduce the
+    single-process step exactly up to the summation order of the all-reduce."""
+    import torch.nn as nn
+
+    from blurred_gan_b200.blurred_gan import BlurredWGAN
+
+    class Gen(nn.Module):
+        latent_size = 6
+
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(6, 3 * 12 * 12)
+
+        def forward(self, z):
+            return torch.tanh(self.fc(z)).view(-1, 3, 12, 12)
+
+    torch.manual_seed(11)
+    gen, critic = Gen(), nn.Sequential(nn.Flatten(), nn.Linear(3 * 12 * 12, 1))
+    hp = BlurredWGAN.HyperParameters(learning_rate=1e-2, batch_size=8, global_batch_size=8, initial_blur_std=1.5)
+    return gen, critic, hp, blur
+
+
+def _step_worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from test_wgan_harness import OracleBlur2D
+
+    from blurred_gan_b200.blurred_gan import BlurredWGAN
+    from blurred_gan_b200.dist import allreduce_gradients
+
+    gen, critic, hp, blur = _tiny_gan(OracleBlur2D(1.5))
+    gan = BlurredWGAN(gen, critic, hp, blur=blur, grad_sync=allreduce_gradients if world > 1 else None)
+    torch.manual_seed(5)
+    reals = torch.rand(8, 3, 12, 12) * 2 - 1
+    latents = [torch.rand(8, 6) for _ in range(4)]  # critic step and generator step of two batches
+    lo, hi = rank * 8 // world, (rank + 1) * 8 // world
+    draws = iter(latents)
+    gan.latents_batch = lambda: next(draws)[lo:hi]  # every rank sees its shard of the same global latents
+    for _ in range(2):
+        gan.train_on_batch(reals[lo:hi])
+    state = {k: v.detach().clone() for k, v in list(gan.generator.state_dict().items()) + list(gan.discriminator[1].state_dict().items())}
+    torch.save(state, os.path.join(out_dir, "w%d_r%d.pt" % (world, rank)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_sharded_train_step_equals_the_single_process_step(tmp_path):
+    """SURVEY 8e / configs[2]: the batch is sharded over ranks, the losses are divided by the *global* batch size
+    (wgan.py:130,157), the gradients are summed over ranks (dist.allreduce_gradients) -- two Adam steps later every rank
+    holds the weights of the single-process run on the whole batch."""
+    mp.spawn(_step_worker, args=(WORLD, _free_port(), str(tmp_path)), nprocs=WORLD, join=True)
+    _step_worker(0, 1, 0, str(tmp_path))
+    single = torch.load(tmp_path / "w1_r0.pt")
+    ranks = [torch.load(tmp_path / ("w%d_r%d.pt" % (WORLD, r))) for r in range(WORLD)]
+    for k, want in single.items():
+        assert torch.equal(ranks[0][k], ranks[1][k]), k          # the ranks stay in lock-step
+        assert torch.allclose(ranks[0][k], want, rtol=1e-5, atol=1e-6), k
+    # and the step did move the weights
+    gen0 = _tiny_gan(None)[0]
+    assert not torch.allclose(single["fc.weight"], gen0.state_dict()["fc.weight"])
