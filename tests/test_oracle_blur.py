@@ -110,3 +110,33 @@ def test_live_reference_agrees_with_oracle():
         assert np.abs(y - y_ref).max() <= 2e-6 * np.abs(y_ref).max()
         y_port = bo.blur_conv2d_port(torch.from_numpy(x), std).numpy()
         assert np.abs(y_port - y_ref).max() <= 2e-6 * np.abs(y_ref).max()
+
+
+@pytest.mark.parametrize("shape,std", [((2, 20, 24, 3), 2.0), ((1, 128, 128, 3), 5.0), ((2, 28, 28, 1), 23.0), ((1, 37, 50, 3), 0.01)])
+def test_tf_rule_oracle_against_two_independent_convolutions(shape, std):
+    """TensorFlow cannot run here, so the TF-rule oracle is pinned from two sides instead: its taps by the table of SURVEY
+    A.3 (above), its arithmetic -- depthwise, stride 1, SAME zero padding, vertical pass then horizontal pass,
+    gaussian_blur.py:116-130 -- by ATen's grouped conv2d and by scipy.ndimage.correlate1d(mode='constant'), two library
+    implementations that share no code with the oracle's numpy loops."""
+    import scipy.ndimage
+    import torch
+    import torch.nn.functional as F
+
+    x = uniform_pm1(9, shape)
+    n, h, w, c = shape
+    taps = bo.taps_for(bo.RULE_TF, std, h, w)
+    r = len(taps) // 2
+    got = bo.blur_images_tf_ref(x, std)
+    assert got.shape == x.shape and got.dtype == np.float32
+    # ATen: depthwise convolutions in fp64 (an odd kernel with padding r is exactly SAME padding)
+    t = torch.from_numpy(x.astype(np.float64)).permute(0, 3, 1, 2)
+    k = torch.from_numpy(taps.astype(np.float64))
+    yv = F.conv2d(t, k.view(1, 1, -1, 1).repeat(c, 1, 1, 1), padding=(r, 0), groups=c)
+    yt = F.conv2d(yv, k.view(1, 1, 1, -1).repeat(c, 1, 1, 1), padding=(0, r), groups=c).permute(0, 2, 3, 1).numpy()
+    scale = np.abs(yt).max()
+    assert np.abs(got - yt).max() <= 2e-6 * scale
+    # scipy: correlate along H, then along W, zeros outside
+    ys = scipy.ndimage.correlate1d(x.astype(np.float64), taps.astype(np.float64), axis=1, mode="constant", cval=0.0)
+    ys = scipy.ndimage.correlate1d(ys, taps.astype(np.float64), axis=2, mode="constant", cval=0.0)
+    assert np.abs(got - ys).max() <= 2e-6 * scale
+    assert np.abs(yt - ys).max() <= 1e-12 * scale  # (the two references agree with each other to fp64 rounding)
