@@ -69,6 +69,8 @@ def main():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--std", type=float, default=5.0)
+    p.add_argument("--fused-critic", action="store_true",
+                   help="SURVEY 8f row N3: one blur launch for the generated and the real batch, interpolates between the blurred batches")
     a = p.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -82,7 +84,7 @@ def main():
         torch.manual_seed(0)  # identical initial weights on every rank
         hp = BlurredWGANGP.HyperParameters(batch_size=per_rank, global_batch_size=a.global_batch, initial_blur_std=a.std)
         blur = GaussianBlur2D(a.std) if kind == "blur" else _Identity()
-        gan = BlurredWGANGP(nets.CelebaGenerator(), nets.CelebaDiscriminator(), hp, blur=blur,
+        gan = BlurredWGANGP(nets.CelebaGenerator(), nets.CelebaDiscriminator(), hp, blur=blur, fused_critic=a.fused_critic and kind == "blur",
                             grad_sync=allreduce_gradients if world > 1 else None).cuda()
         ctl = callbacks.BlurDecayController(total_n_training_examples=202599 * 10, max_value=a.std)
         ctl.set_model(gan)
@@ -97,7 +99,7 @@ def main():
             "metric": "blurred WGAN-GP train step images/s at 128x128x3", "value": a.global_batch / (ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg3: BlurredWGANGP.train_on_batch, CelebA-128 DCGAN nets, global batch %d sharded over %d GPU(s), std %.2f" % (
-                a.global_batch, world, a.std), "blur_applications_per_step": 7},
+                a.global_batch, world, a.std), "blur_applications_per_step": 6 if a.fused_critic else 7, "fused_critic": bool(a.fused_critic)},
             "ms_per_step_without_blur": ms_id, "blur_share_of_step": max(ms - ms_id, 0.0) / ms,
             "last_metrics": metrics}), flush=True)
     if world > 1:
