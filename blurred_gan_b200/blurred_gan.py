@@ -48,11 +48,14 @@ def BlurredVariant(some_gan_base_class):
             return self.blur.std
 
         def assign_std(self, value: float) -> None:
-            """``model.std.assign(value)`` (reference callbacks.py:62) without a device round trip."""
-            if hasattr(self.blur, "assign"):
-                self.blur.assign(value)
-            else:
-                self.blur.std.data.fill_(float(value))
+            """``model.std.assign(value)`` (reference callbacks.py:62)."""
+            for name in ("assign", "set_std"):
+                fn = getattr(self.blur, name, None)
+                if fn is not None:
+                    fn(value)
+                    return
+            with torch.no_grad():  # (an in-place op on the Parameter itself: bumps its version, unlike `.data` writes)
+                self.blur.std.fill_(float(value))
 
         def discriminator_step(self, reals):
             try:

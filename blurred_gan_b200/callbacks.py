@@ -1,8 +1,8 @@
 """Sigma controllers of the reference (``callbacks.py:45-135``) for the torch train-step harness.
 
-Host-side control only: they decide the next ``std`` and write it into ``model.std`` before a batch.  The write goes
-through ``model.assign_std`` so that the blur layer keeps a host shadow of sigma -- the radius fixes the launch
-geometry, and reading sigma back from the device every step would serialise the stream.
+Host-side control only: they decide the next ``std`` and write it into ``model.std`` before a batch
+(``model.assign_std``).  The blur layers keep that Parameter in host memory -- the radius fixes the launch geometry, and
+reading sigma back from the device every step would serialise the stream.
 """
 from __future__ import annotations
 
@@ -100,3 +100,5 @@ class AdaptiveBlurController:
             self.decrease_blur_std(batch)
         if self.std < self.min_value:
             self.stop_training = True
+            if self.model is not None:
+                self.model.stop_training = True  # what the reference sets (callbacks.py:134) and a Keras-style loop checks

@@ -103,6 +103,25 @@ def positions_packed_for_round(n_images: int, level_sizes, nhood_size: int, nhoo
     return out
 
 
+def check_lockstep(values, group=None, world=None) -> None:
+    """Raise unless every rank holds the same `values` (a short list of integers < 2^52, e.g. the feed count and the
+    hash of the fed minibatch sizes).  `positions_packed_for_round` replays the other ranks' draws with this rank's own
+    sizes, and `sliced_wasserstein` relies on all ranks drawing the same directions: both only hold in lock step."""
+    if (world if world is not None else world_info(group)[1]) <= 1:
+        return
+    v = torch.tensor([float(x) for x in values], dtype=torch.float64)
+    t = torch.cat([v, -v])
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)  # max(v) and -min(v)
+    t = t.cpu()
+    k = len(values)
+    if not torch.equal(t[:k], -t[k:]):
+        raise RuntimeError("sliced_wasserstein.API: ranks fed different numbers or sizes of minibatches (feeds, size hash: this rank %s, "
+                           "max over ranks %s, min %s); a multi-rank evaluation needs the same sequence of minibatch sizes on every rank"
+                           % (list(values), t[:k].tolist(), (-t[k:]).tolist()))
+
+
 def direction_block(total_dirs: int, rank: int, world: int) -> slice:
     """The block of projection directions (columns of the [dim, repeats * dirs_per_repeat] matrix) owned by `rank`."""
     lo, hi = shard_range(total_dirs, rank, world)

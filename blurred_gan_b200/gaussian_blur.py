@@ -116,21 +116,29 @@ class GaussianBlur2D(nn.Module):
 
     def __init__(self, initial_std: float = 0.01, *args, **kwargs):
         super().__init__()
+        # Kept in HOST memory whatever device the layer is moved to (`_apply` below): the kernel-size rule needs sigma
+        # on the host before every launch, a CPU scalar is free to read and every write to it -- `assign`, `fill_`,
+        # `.data.fill_`, `load_state_dict` -- is seen by the next forward (no cached copy that could go stale).
         self.std = nn.Parameter(torch.tensor(float(initial_std), dtype=torch.float32), requires_grad=False)
-        self._std_cache = (None, None, float(initial_std))
+
+    def _apply(self, fn, recurse=True):
+        std = self._parameters.pop("std")
+        try:
+            super()._apply(fn, recurse)
+        finally:
+            self._parameters["std"] = std
+        return self
 
     def std_value(self) -> float:
-        p = self.std
-        key = (p._version, p.data_ptr())
-        if (self._std_cache[0], self._std_cache[1]) != key:
-            self._std_cache = (key[0], key[1], float(p.detach().item()))
-        return self._std_cache[2]
+        """Current sigma as a Python float.  No device synchronisation unless a caller replaced `std` by a CUDA tensor."""
+        return float(self.std.detach().reshape(-1)[0])
 
     def assign(self, value: float) -> None:
-        """``model.std.assign(value)`` of the reference's controllers, without a device->host sync."""
+        """``model.std.assign(value)`` of the reference's controllers (``callbacks.py:60-62``)."""
         with torch.no_grad():
             self.std.fill_(float(value))
-        self._std_cache = (self.std._version, self.std.data_ptr(), float(_F32(value)))
+
+    set_std = assign
 
     def forward(self, image: torch.Tensor) -> torch.Tensor:
         return blur_images(image, self.std_value())

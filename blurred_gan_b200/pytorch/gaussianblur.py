@@ -53,24 +53,33 @@ def appropriate_kernel_size(std) -> int:
 class GaussianBlur(nn.Module):
     def __init__(self, std: float = 2.0):
         super().__init__()
-        # frozen Parameter named `std`, shape [1]: part of state_dict, assigned by the sigma controllers
+        # frozen Parameter named `std`, shape [1]: part of state_dict, assigned by the sigma controllers.
+        # It stays in HOST memory whatever device the module is moved to (`_apply` below): the kernel-size rule
+        # (`:43-57`) needs sigma on the host before every launch -- radius and kernel choice are launch parameters --
+        # so a device-resident std would cost a device->host synchronisation per change, and a cached host copy goes
+        # stale when the Parameter is written through `.data` (which does not bump `_version`).  Reading a CPU scalar is
+        # free and sees every write, whichever way it was made.
         self.std = nn.Parameter(torch.Tensor([std]), requires_grad=False)
         self._image_size = None
-        self._std_cache = (None, None, float(std))  # (version, data_ptr, host value)
 
-    # -- host shadow of std: one device->host read per *change* of the Parameter, not per forward ---------
+    def _apply(self, fn, recurse=True):
+        std = self._parameters.pop("std")
+        try:
+            super()._apply(fn, recurse)
+        finally:
+            self._parameters["std"] = std
+        return self
+
     def std_value(self) -> float:
-        p = self.std
-        key = (p._version, p.data_ptr())
-        if (self._std_cache[0], self._std_cache[1]) != key:
-            self._std_cache = (key[0], key[1], float(p.detach().reshape(-1)[0].item()))
-        return self._std_cache[2]
+        """Current sigma as a Python float.  No device synchronisation unless a caller replaced `std` by a CUDA tensor."""
+        return float(self.std.detach().reshape(-1)[0])
 
     def set_std(self, value: float) -> None:
-        """Assign a new std without a device->host synchronisation (what a sigma controller should call)."""
+        """Assign a new std (what a sigma controller calls every batch; reference ``callbacks.py:60-62``)."""
         with torch.no_grad():
             self.std.fill_(float(value))
-        self._std_cache = (self.std._version, self.std.data_ptr(), float(np.float32(value)))
+
+    assign = set_std  # the name the reference's controllers use (``model.std.assign``)
 
     @property
     def kernel(self) -> torch.Tensor:

@@ -222,11 +222,13 @@ class API:
         self._slabs = None  # per level: one growing [capacity, C, nhood, nhood] array, filled in place by the fused feed
         self._sums = None  # per level: fp64 [sum_c..., sumsq_c..., rows]; the statistics are accumulated on the device
         self._rows = [0 for _ in self.resolutions]
+        self._feed_log = [0, 0]  # (number of feeds, rolling hash of their minibatch sizes): must agree across ranks
 
     def feed(self, mode, minibatch):
         mb = _to_device(minibatch, self.device)
         n, c = mb.shape[0], mb.shape[1]
         assert mb.dim() == 4 and c == 3
+        self._feed_log = [self._feed_log[0] + 1, (self._feed_log[1] * 1000003 + n) % (1 << 50)]
         n_levels = len(self.resolutions)
         h, w = mb.shape[2], mb.shape[3]
         sizes = [(h >> lod, w >> lod) for lod in range(n_levels)]
@@ -280,6 +282,9 @@ class API:
         return _dist.all_gather_rows(desc.reshape(desc.shape[0], -1), self.group)
 
     def end(self, mode):
+        # every rank replays the position draws of all ranks with its OWN minibatch sizes (dist.positions_packed_for_round):
+        # ranks that fed different sizes or counts would silently desynchronise the random streams (and the directions)
+        _dist.check_lockstep(self._feed_log, self.group if self.world > 1 else None, self.world)
         if self._slabs is not None:
             # (a slab with more than 25 % slack is copied once so that the set kept for later comparisons does not pin the slack)
             local = [slab[:rows] if 4 * rows >= 3 * slab.shape[0] else slab[:rows].clone() for slab, rows in zip(self._slabs, self._rows)]

@@ -39,6 +39,13 @@ def _worker(rank, world, port, out_dir):
     t = torch.full((3 + rank, 2), float(rank))
     g = bd.all_gather_rows(t)
     assert g.shape == (3 + 4, 2) and torch.equal(g[:3], torch.zeros(3, 2)) and torch.equal(g[3:], torch.ones(4, 2))
+    # ---- lock-step check: equal feed logs pass, a rank that fed another minibatch size is caught on every rank ----
+    bd.check_lockstep([3, 12345])
+    try:
+        bd.check_lockstep([3, 12345 + rank])
+        raise SystemExit("check_lockstep accepted ranks with different feed logs")
+    except RuntimeError as exc:
+        assert "different numbers or sizes" in str(exc)
     # ---- distributed SWD protocol, oracle compute ------------------------------------------------------------
     reals = uniform_pm1(41, (8, 3, 32, 32))
     fakes = (0.7 * uniform_pm1(42, (8, 3, 32, 32)) + 0.05).astype(np.float32)

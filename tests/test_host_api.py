@@ -23,8 +23,19 @@ def test_torch_module_surface_and_state():
     m2.set_std(5.0)
     assert m2.kernel_size == 25 and float(m2.std) == 5.0
     with torch.no_grad():
-        m2.std.fill_(0.5)  # a controller writing the Parameter directly is picked up through its version counter
+        m2.std.fill_(0.5)  # a controller writing the Parameter directly
     assert m2.std_value() == 0.5 and m2.kernel_size == 3
+    # writes through `.data` do not bump the Parameter's version counter: they must be seen all the same
+    v = m2.std._version
+    m2.std.data.fill_(3.0)
+    assert m2.std._version == v and m2.std_value() == 3.0 and m2.kernel_size == 15
+    m2.std.data.copy_(torch.tensor([8.0]))
+    assert m2.std_value() == 8.0 and m2.kernel_size == 41
+    m2.assign(2.0)  # the reference controllers' name (callbacks.py:60-62)
+    assert m2.std_value() == 2.0
+    # std stays in host memory under module moves / casts (read every forward without a device synchronisation)
+    m3 = m2.to(torch.float64)
+    assert m3.std.dtype == torch.float32 and m3.std.device.type == "cpu" and list(m3.state_dict().keys()) == ["std"]
 
 
 def test_torch_module_kernel_matches_reference(golden_taps):
@@ -70,6 +81,11 @@ def test_tf_helpers_match_oracle():
     assert list(layer.state_dict().keys()) == ["std"] and layer.std_value() == pytest.approx(0.05)
     layer.assign(3.0)
     assert layer.std_value() == 3.0
+    layer.std.data.fill_(1.5)  # `.data` writes (no version bump) are seen too
+    assert layer.std_value() == 1.5
+    layer.std.data.copy_(torch.tensor(0.25))
+    assert layer.std_value() == 0.25
+    assert layer.to(torch.float64).std.dtype == torch.float32
 
 
 def test_swd_surface():

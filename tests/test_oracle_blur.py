@@ -95,20 +95,43 @@ def test_operator_is_self_adjoint_and_darkens_borders():
     assert b1[0, 0, 0, 0] == pytest.approx(0.310, abs=2e-3) and b1[0, 0, 32, 32] == pytest.approx(1.0, abs=1e-6)
 
 
+_LIVE_REFERENCE_SCRIPT = """
+import sys
+import numpy as np
+import torch
+with open("/root/reference/pytorch/gaussianblur.py") as f:
+    head = "".join(f.readlines()[:72])
+ns = {}
+exec(compile(head, "ref_head", "exec"), ns)
+data = np.load(sys.argv[1])
+out = {}
+for std in data["stds"]:
+    out["y_%g" % std] = ns["GaussianBlur"](float(std))(torch.from_numpy(data["x"])).numpy()
+np.savez(sys.argv[2], **out)
+"""
+
+
 @needs_reference
-def test_live_reference_agrees_with_oracle():
+def test_live_reference_agrees_with_oracle(tmp_path):
+    """The unmodified reference head runs in a CHILD process (isolated interpreter, empty environment, scratch working
+    directory): /root/reference is untrusted content, whatever it does at import time stays out of the test process."""
+    import subprocess
+    import sys
+
     import torch
 
-    with open("/root/reference/pytorch/gaussianblur.py") as f:
-        head = "".join(f.readlines()[:72])
-    ns = {}
-    exec(compile(head, "ref_head", "exec"), ns)
     x = uniform_pm1(77, (4, 1, 33, 40))
-    for std in (0.7, 3.3, 15.0):
-        y_ref = ns["GaussianBlur"](std)(torch.from_numpy(x)).numpy()
-        y = bo.gaussian_blur_torch_ref(x, std)
+    stds = np.array([0.7, 3.3, 15.0])
+    np.savez(tmp_path / "in.npz", x=x, stds=stds)
+    subprocess.run([sys.executable, "-I", "-c", _LIVE_REFERENCE_SCRIPT, str(tmp_path / "in.npz"), str(tmp_path / "out.npz")],
+                   check=True, cwd=str(tmp_path), env={"PATH": "/usr/bin:/bin", "OMP_NUM_THREADS": "4"}, timeout=300,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ref = np.load(tmp_path / "out.npz")
+    for std in stds:
+        y_ref = ref["y_%g" % std]
+        y = bo.gaussian_blur_torch_ref(x, float(std))
         assert np.abs(y - y_ref).max() <= 2e-6 * np.abs(y_ref).max()
-        y_port = bo.blur_conv2d_port(torch.from_numpy(x), std).numpy()
+        y_port = bo.blur_conv2d_port(torch.from_numpy(x), float(std)).numpy()
         assert np.abs(y_port - y_ref).max() <= 2e-6 * np.abs(y_ref).max()
 
 

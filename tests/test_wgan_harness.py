@@ -167,6 +167,40 @@ def test_adaptive_controller_tracks_but_does_not_assign_by_default():
     assert float(gan.std.item()) == 23.5  # callbacks.py:102-103: the assignment is disabled in the reference
 
 
+def test_adaptive_controller_stops_the_model_below_min_value():
+    """callbacks.py:133-134: once the tracked sigma falls below min_value the *model's* stop_training flag is raised."""
+    gan = _mnist_gan(OracleBlur2D(1.0), batch=4)
+    ctl = callbacks.AdaptiveBlurController(warmup_n_batches=0, max_value=0.0101, min_value=0.01)
+    ctl.set_model(gan)
+    assert not getattr(gan, "stop_training", False)
+    for b in range(0, 301, 100):
+        ctl.on_batch_end(b, {"fake_scores": 1.0, "real_scores": 1.0})
+    assert ctl.std < 0.01 and ctl.stop_training and gan.stop_training is True
+
+
+def test_assign_std_reaches_layers_without_assign():
+    """a blur layer that only offers `set_std` (or nothing) must still see the controller's value."""
+
+    class OnlySetStd(OracleBlur2D):
+        assign = None
+
+        def set_std(self, value):
+            with torch.no_grad():
+                self.std.fill_(float(value))
+
+    gan = _mnist_gan(OnlySetStd(5.0), batch=4)
+    gan.assign_std(2.5)
+    assert float(gan.std.item()) == 2.5
+
+    class Bare(OracleBlur2D):
+        assign = None
+
+    gan = _mnist_gan(Bare(5.0), batch=4)
+    v = gan.std._version
+    gan.assign_std(1.25)
+    assert float(gan.std.item()) == 1.25 and gan.std._version > v  # an in-place op on the Parameter, not a `.data` write
+
+
 @pytest.mark.gpu
 def test_celeba_step_on_gpu_matches_the_oracle_blur_step(monkeypatch):
     """BASELINE configs[2] shape (small batch): the step through the B200 blur == the step through the oracle blur."""
