@@ -49,7 +49,9 @@ def parse_args():
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--no-swd", action="store_true", help="skip the secondary SWD timing")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-large", action="store_true", help="skip the 1024 x 1024 context rows (BASELINE configs[3])")
     p.add_argument("--swd-images", type=int, default=16384, help="images per set for the secondary SWD timing (BASELINE configs[4]: 16384)")
+    p.add_argument("--swd-cpu-images", type=int, default=512, help="images per set for the SWD CPU baseline (bounded sample)")
     p.add_argument("--stds", type=str, default="", help="comma-separated override of the std sweep (profiling runs)")
     return p.parse_args()
 
@@ -200,6 +202,8 @@ def run_reference_arm(args, stds):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_swd:
+        line["swd"] = {"cpu_baseline": swd_cpu_baseline(args.swd_cpu_images)}
     print(json.dumps(line), flush=True)
 
 
@@ -296,10 +300,13 @@ def run_native(args, stds):
                     ev[i][j][1].record(stream)
         barrier()
     elapsed_ms = e0.elapsed_time(e1)
+    per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(v.item()) / args.steps for v in every]  # names the rank that decides the max
+        elapsed_ms = max(float(v.item()) for v in every)
     images_per_step = BATCH * len(stds)
     value = world * args.steps * images_per_step / (elapsed_ms * 1e-3)
     launches = args.steps * len(stds) * 2
@@ -414,6 +421,39 @@ def run_native(args, stds):
             multi.append({"std": s, "tensors": 2, "two_launches_us": round(res["two_launches"], 2), "one_launch_us": round(res["one_launch"], 2),
                           "one_launch_hbm_frac": round(4 * plane_bytes / (res["one_launch"] * 1e-6) / 1e9 / hbm_peak, 4)})
 
+    # ---- context: BASELINE configs[3], the large-image stress [32, 3, 1024, 1024], sigma 8 / 32 / 64 (TF rule: up to 385 taps)
+    large = None
+    if (world == 1 or rank == 0) and not args.no_large:
+        large = []
+        LN, LH = 32, 1024
+        lbytes = LN * CH * LH * LH * 4
+        xl = [torch.rand(LN, CH, LH, LH, device=dev) * 2 - 1 for _ in range(2)]
+        yl = [torch.empty_like(xl[0]) for _ in range(2)]
+        for s in (8.0, 32.0, 64.0):
+            _, radius, std_eff = _lib.blur_plan(_lib.RULE_TF, s, LH, LH)
+            ws_bytes = lib.bgan_blur2d_workspace_bytes(LN, CH, LH, LH, 0, radius)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(stream):
+                sp = torch.cuda.current_stream().cuda_stream
+
+                def go(i):
+                    _lib.check(lib.bgan_blur2d_f32(xl[i & 1].data_ptr(), yl[i & 1].data_ptr(), LN, CH, LH, LH, 0, _lib.RULE_TF, std_eff, radius, None,
+                                                   ws.data_ptr(), ws_bytes, sp), "cfg4")
+
+                go(0)
+                path = lib.bgan_blur2d_last_path()
+                go(1)
+                c0.record(stream)
+                for i in range(6):
+                    go(i)
+                c1.record(stream)
+            stream.synchronize()
+            us = c0.elapsed_time(c1) / 6 * 1e3
+            large.append({"std": s, "taps": 2 * radius + 1, "path": path, "launch_ms": round(us * 1e-3, 4),
+                          "images_per_s": round(LN / (us * 1e-6), 1), "algorithmic_bytes": 2 * lbytes,
+                          "hbm_frac": round(2 * lbytes / (us * 1e-6) / 1e9 / hbm_peak, 4)})
+        del xl, yl, ws
+
     # ---- e2e through the public module with host buffers ----------------------------------------------
     e2e = None
     if True:
@@ -465,7 +505,7 @@ def run_native(args, stds):
             e2e_step()
         # three windows of e2e_steps steps, the median window is reported: the pipeline is driven by the host (copies, module
         # calls, the autograd thread), and a single hiccup of a shared host otherwise decides the number
-        windows = []
+        windows, windows_local = [], []
         for _ in range(3):
             barrier()
             torch.cuda.synchronize(dev)
@@ -474,65 +514,165 @@ def run_native(args, stds):
                 e2e_step()
             torch.cuda.synchronize(dev)  # (all three streams)
             dt = time.perf_counter() - t0
+            windows_local.append(dt)
             if world > 1:
                 t = torch.tensor([dt], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             windows.append(dt)
         dt = sorted(windows)[1]
+        # The ceiling of this pipeline: the same pinned buffers copied host -> device and device -> host on the two copy
+        # streams, both directions at once, no kernels -- measured at the same world size in the same run (all ranks copy
+        # at the same time, like in the timed windows above).
+        def copy_only():
+            for i in range(len(stds)):
+                slot = i & 1
+                with torch.cuda.stream(s_in):
+                    dbuf[slot][0].copy_(xh, non_blocking=True)
+                    dbuf[slot][1].copy_(gh, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    yh.copy_(dbuf[1 - slot][0], non_blocking=True)
+                    gxh.copy_(dbuf[1 - slot][1], non_blocking=True)
+
+        copy_only()
+        cwin = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                copy_only()
+            torch.cuda.synchronize(dev)
+            cwin.append(time.perf_counter() - t0)
+        cdt_local = sorted(cwin)[1]
+        dt_local = sorted(windows_local)[1]
+        per_dir = 2 * plane_bytes * len(stds) * e2e_steps  # bytes per direction per rank per window
+        stats = torch.tensor([dt_local, cdt_local], device=dev, dtype=torch.float64)
+        if world > 1:
+            gathered = [torch.zeros_like(stats) for _ in range(world)]
+            dist.all_gather(gathered, stats)
+        else:
+            gathered = [stats]
+        per_rank = [g.tolist() for g in gathered]
+        cdt = max(r[1] for r in per_rank)
         e2e = {"value": world * e2e_steps * images_per_step / dt, "unit": "images/s",
                "h2d_bytes_per_step": 2 * plane_bytes * len(stds), "d2h_bytes_per_step": 2 * plane_bytes * len(stds),
-               "steps": e2e_steps, "windows_s": [round(w, 4) for w in windows], "api": "GaussianBlur(std)(x); y.backward(g); pinned host x, g -> host y, grad_x; H2D | blur | D2H on three streams"}
+               "steps": e2e_steps, "windows_s": [round(w, 4) for w in windows],
+               "achieved_gbs_per_direction_per_rank": [round(per_dir / r[0] / 1e9, 2) for r in per_rank],
+               "copy_ceiling": {"what": "the same pinned buffers, H2D and D2H at once on the two copy streams, no kernels, all ranks at the same time",
+                                "gbs_per_direction_per_rank": [round(per_dir / r[1] / 1e9, 2) for r in per_rank],
+                                "images_per_s_if_copy_bound": round(world * e2e_steps * images_per_step / cdt, 1)},
+               "frac_of_copy_ceiling": round(cdt / dt, 4),
+               "api": "GaussianBlur(std)(x); y.backward(g); pinned host x, g -> host y, grad_x; H2D | blur | D2H on three streams"}
         launches += 0  # e2e launches are outside the timed `value` region
 
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": elapsed_ms / args.steps, "ms_per_step_per_rank": [round(v, 5) for v in per_rank_ms],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "stds": stds, "images_per_step": images_per_step, "launches_per_step": 2 * len(stds),
                    "l2": "5 rotating buffer sets (1.0 GB per GPU) > 126 MB L2; one CUDA graph per step",
                    "parallelism": "batch sharded, %d x 256 images, no collective" % world},
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches * world, "roofline": roofline, "per_std": per_std,
-        "copy_reference": copy_ref, "nhwc_tf_rule": nhwc, "multi_tensor_launch": multi,
+        "copy_reference": copy_ref, "nhwc_tf_rule": nhwc, "multi_tensor_launch": multi, "large_image_cfg4": large,
     }
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(stds)
-    if rank == 0 and not args.no_swd and world == 1:
+    if not args.no_swd:  # every rank takes part (sharded feed, NCCL exchange)
         try:
-            line["swd"] = swd_timing(args.swd_images, dev)
+            swd = swd_timing(args.swd_images, dev, rank, world, hbm_peak)
         except Exception as exc:  # secondary measurement: never lose the headline line
-            line["swd"] = {"error": repr(exc)}
+            swd = {"error": repr(exc)}
+        if rank == 0 and not args.no_cpu_baseline and world == 1 and "error" not in swd:
+            swd["cpu_baseline"] = swd_cpu_baseline(args.swd_cpu_images)
+            swd["speedup_vs_cpu_extrapolated"] = round(swd["cpu_baseline"]["extrapolated_s_at_16384"] * (swd["images_per_set"] / 16384.0) / swd["eval_s"], 1)
+        line["swd"] = swd
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def swd_timing(n_images, dev):
-    """Secondary: sliced_wasserstein.API on n_images reals + n_images fakes of 3x128x128 (inputs resident in HBM)."""
-    import torch
+class _EventTimer:
+    """Device time of selected calls: a CUDA event pair around every call (no synchronisation; summed after the run)."""
 
+    def __init__(self):
+        self.pairs = {}
+        self.patched = []
+
+    def wrap(self, mod, name):
+        import torch
+
+        fn = getattr(mod, name)
+        pairs = self.pairs.setdefault(name, [])
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            pairs.append((e0, e1))
+            return out
+
+        setattr(mod, name, timed)
+        self.patched.append((mod, name, fn))
+
+    def restore(self):
+        for mod, name, fn in self.patched:
+            setattr(mod, name, fn)
+        self.patched = []
+
+    def reset(self):
+        for v in self.pairs.values():
+            del v[:]
+
+    def seconds(self, name):
+        return sum(a.elapsed_time(b) for a, b in self.pairs.get(name, [])) * 1e-3
+
+    def calls(self, name):
+        return len(self.pairs.get(name, []))
+
+
+# HBM bytes the radix sort moves per key (csrc/sort.cu): 4 digit passes x (scatter read + write) + the histogram reads
+SORT_BYTES_PER_KEY = 48
+
+
+def swd_timing(n_images, dev, rank=0, world=1, hbm_peak=None):
+    """BASELINE configs[4]: sliced_wasserstein.API on n_images reals + n_images fakes of 3x128x128, the images sharded
+    over the ranks (rank r feeds the global minibatches k * world + r), inputs resident in HBM.  With world > 1 the
+    channel statistics are all-reduced, the standardised descriptors all-gathered over NCCL and every rank sorts its own
+    512 / world directions (blurred_gan_b200/dist.py).  Time = wall clock of the whole evaluation, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from blurred_gan_b200 import dist as bd
+    from blurred_gan_b200 import ops
     from blurred_gan_b200 import sliced_wasserstein as sw
 
     mb = 64
-    torch.manual_seed(5)
-    reals = torch.rand(n_images, 3, 128, 128, device=dev) * 2 - 1
-    fakes = (torch.rand(n_images, 3, 128, 128, device=dev) * 2 - 1) * 0.9
-    out = {}
+    rounds = n_images // (mb * world)
+    per_rank = rounds * mb
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5 + rank)
+    reals = torch.rand(per_rank, 3, 128, 128, device=dev, generator=gen) * 2 - 1
+    fakes = (torch.rand(per_rank, 3, 128, 128, device=dev, generator=gen) * 2 - 1) * 0.9
+    timer = _EventTimer()
 
     def run():
         np.random.seed(0)
-        api = sw.API((3, 128, 128))
+        api = sw.API((3, 128, 128), distributed=world > 1)
         t = {}
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         api.begin("reals")
-        for i in range(0, n_images, mb):
+        for i in range(0, per_rank, mb):
             api.feed("reals", reals[i : i + mb])
         api.end("reals")
         api.begin("fakes")
-        for i in range(0, n_images, mb):
+        for i in range(0, per_rank, mb):
             api.feed("fakes", fakes[i : i + mb])
         torch.cuda.synchronize(dev)
         t["feed_s"] = time.perf_counter() - t0
@@ -541,14 +681,71 @@ def swd_timing(n_images, dev):
         t["total_s"] = time.perf_counter() - t0
         return res, t
 
-    run()  # warm-up
+    run()  # warm-up (allocator, NCCL channels)
     res, t = run()
-    rows = n_images * 128
-    out.update({"images_per_set": n_images, "eval_s": round(t["total_s"], 4), "feed_s": round(t["feed_s"], 4),
-                "end_s": round(t["total_s"] - t["feed_s"], 4), "sort_keys": 2 * 4 * 4 * 128 * rows,
-                "sort_gkeys_per_s_incl_project": round(2 * 4 * 4 * 128 * rows / max(t["total_s"] - t["feed_s"], 1e-9) / 1e9, 3),
-                "result_x1e3": [float(v) for v in res], "note": "host RNG draws (reference order) are inside eval_s"})
+    # third run with CUDA-event pairs around the library calls: device time per phase (not part of eval_s)
+    for name in ("swd_sort_", "swd_project", "swd_absdiff_sum", "swd_normalise_", "swd_feed"):
+        timer.wrap(ops, name)
+    timer.wrap(bd, "all_gather_rows")
+    try:
+        run()
+        torch.cuda.synchronize(dev)
+        phases = {name: timer.seconds(name) for name in timer.pairs}
+        calls = {name: timer.calls(name) for name in timer.pairs}
+    finally:
+        timer.restore()
+    times = torch.tensor([t["total_s"], t["feed_s"]] + [phases[k] for k in sorted(phases)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    times = times.tolist()
+    total_s, feed_s = times[0], times[1]
+    phases = dict(zip(sorted(phases), times[2:]))
+    rows = rounds * world * mb * 128                   # descriptors per level per set, whole job
+    keys_job = 2 * 4 * 4 * 128 * rows                  # A and B, 4 levels, 512 directions (the zero real-vs-real pass is not counted)
+    keys_rank = keys_job // world
+    desc_bytes_job = 2 * 4 * rows * 147 * 4            # all-gather payload: every rank ends up with all of it
+    out = {"images_per_set": rounds * world * mb, "n_gpus": world, "eval_s": round(total_s, 4), "feed_s": round(feed_s, 4),
+           "end_s": round(total_s - feed_s, 4), "images_per_s": round(2 * rounds * world * mb / total_s, 1),
+           "result_x1e3": [float(v) for v in res],
+           "device_time_s": {k: round(v, 4) for k, v in phases.items()}, "calls": calls,
+           "sort": {"keys_whole_job": keys_job, "keys_per_rank": keys_rank, "sort_s": round(phases["swd_sort_"], 4),
+                    "gkeys_per_s_per_gpu": round(keys_rank / max(phases["swd_sort_"], 1e-9) / 1e9, 2),
+                    "gkeys_per_s_whole_job": round(keys_job / max(phases["swd_sort_"], 1e-9) / 1e9, 2),
+                    "hbm_bytes_per_key": SORT_BYTES_PER_KEY,
+                    "hbm_gbs": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_"], 1e-9) / 1e9, 1),
+                    "hbm_frac": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_"], 1e-9) / 1e9 / hbm_peak, 4) if hbm_peak else None},
+           "note": "host RNG draws (reference order) are inside eval_s; device_time_s: CUDA-event pairs around the calls in a separate run"}
+    if world > 1:
+        ag = phases["all_gather_rows"]
+        recv = desc_bytes_job * (world - 1) // world
+        out["all_gather"] = {"payload_bytes_whole_set": desc_bytes_job, "received_bytes_per_rank": recv, "device_time_s": round(ag, 4),
+                             "gbs_received_per_rank": round(recv / max(ag, 1e-9) / 1e9, 1),
+                             "note": "torch.distributed all_gather_into_tensor over NCCL, 8 calls (4 levels x 2 sets); device time incl. the wait for the slowest rank"}
     return out
+
+
+def swd_cpu_baseline(n_images=512):
+    """The reference's own path (oracle restatement of sliced_wasserstein.API, numpy) on the host, on a bounded sample."""
+    from oracle import swd_oracle as so
+
+    rs = np.random.RandomState(5)
+    reals = (rs.rand(n_images, 3, 128, 128) * 2 - 1).astype(np.float32)
+    fakes = ((rs.rand(n_images, 3, 128, 128) * 2 - 1) * 0.9).astype(np.float32)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    api = so.API((3, 128, 128))
+    for mode, data in (("reals", reals), ("fakes", fakes)):
+        api.begin(mode)
+        for i in range(0, n_images, 64):
+            api.feed(mode, data[i : i + 64].copy())
+        res = api.end(mode)
+    dt = time.perf_counter() - t0
+    return {"value": dt, "unit": "s", "images_per_set": n_images, "images_per_s": round(2 * n_images / dt, 2), "cores": os.cpu_count() or 1,
+            "kind": "port", "result_x1e3": [float(v) for v in res],
+            "sample": "oracle/swd_oracle.API (numpy restatement of sliced_wasserstein.py:98-133) on 2 x %d images; numpy's sort is single-threaded, "
+                      "BLAS matmul uses the host threads" % n_images,
+            "extrapolated_s_at_16384": round(dt * 16384 / n_images, 1),
+            "extrapolation": "linear in the image count (a lower bound: the sort, ~90 %% of it, grows as n log n)"}
 
 
 def main():

@@ -141,9 +141,55 @@ def make_swd(sw):
     np.savez_compressed(os.path.join(HERE, "swd.npz"), **out)
 
 
+SWD_LARGE = dict(n=2048, mb=64, seed_reals=61, seed_fakes=62, np_seed=0)
+
+
+def swd_large_inputs():
+    """2 x 2048 images of 3 x 128 x 128 (BASELINE-like scale: 262,144 descriptors per level and set, i.e. 64 sort tiles per
+    direction and 2048 row tiles of the tensor-core projection).  The GPU test regenerates them from the same seeds."""
+    c = SWD_LARGE
+    reals = swd_input(c["seed_reals"], (c["n"], 3, 128, 128))
+    fakes = (0.9 * swd_input(c["seed_fakes"], (c["n"], 3, 128, 128))).astype(np.float32)
+    fakes[:, :, ::2] *= 0.8
+    return reals, fakes
+
+
+def make_swd_large(sw):
+    """The unmodified reference `API` on 2 x 2048 images (about two minutes on 8 cores): 2 x 5 floats."""
+    c = SWD_LARGE
+    reals, fakes = swd_large_inputs()
+    np.random.seed(c["np_seed"])
+    api = sw.API((3, 128, 128))
+    api.begin("reals")
+    for i in range(0, c["n"], c["mb"]):
+        api.feed("reals", reals[i : i + c["mb"]].copy())
+    r0 = api.end("reals")
+    api.begin("fakes")
+    for i in range(0, c["n"], c["mb"]):
+        api.feed("fakes", fakes[i : i + c["mb"]].copy())
+    r1 = api.end("fakes")
+    np.savez_compressed(os.path.join(HERE, "swd_large.npz"), api_reals=np.array(r0, dtype=np.float64), api_fakes=np.array(r1, dtype=np.float64),
+                        config=np.array([c["n"], c["mb"], c["seed_reals"], c["seed_fakes"], c["np_seed"]], dtype=np.int64))
+
+
+def make_swd_downscale(sw):
+    """`downscale_minibatch` (sliced_wasserstein.py:55-61; module surface, not called by `API`) on uint8-range images."""
+    rs = np.random.RandomState(71)
+    x = rs.randint(0, 256, size=(3, 3, 32, 48)).astype(np.uint8)
+    out = {"x": x}
+    for lod in (1, 2, 3):
+        out["lod%d" % lod] = sw.downscale_minibatch(x, lod)
+    np.savez_compressed(os.path.join(HERE, "swd_downscale.npz"), **out)
+
+
 if __name__ == "__main__":
-    make_blur(load_reference_blur())
-    make_swd(load_reference_swd())
+    if "--swd-downscale" in sys.argv:
+        make_swd_downscale(load_reference_swd())
+    elif "--swd-large" in sys.argv:  # slow; kept out of the default run
+        make_swd_large(load_reference_swd())
+    else:
+        make_blur(load_reference_blur())
+        make_swd(load_reference_swd())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -96,3 +96,18 @@ def test_live_reference_agrees_with_oracle():
     d_ref = ref.get_descriptors_for_minibatch(x, 7, 16)
     d = so.get_descriptors_for_minibatch(x, 7, 16, np.random.RandomState(4))
     np.testing.assert_array_equal(d_ref, d)
+
+
+def test_downscale_minibatch_matches_reference_golden():
+    """sliced_wasserstein.py:55-61 (module surface; `API` does not call it): box filter 2^lod, round half to even, uint8."""
+    import os
+
+    from conftest import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "swd_downscale.npz"))
+    x = g["x"]
+    assert so.downscale_minibatch(x, 0) is x
+    for lod in (1, 2, 3):
+        got = so.downscale_minibatch(x, lod)
+        assert got.dtype == np.uint8 and got.shape == (3, 3, 32 >> lod, 48 >> lod)
+        np.testing.assert_array_equal(got, g["lod%d" % lod])

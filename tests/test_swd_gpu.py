@@ -210,6 +210,48 @@ def test_api_matches_oracle_larger():
     np.testing.assert_allclose(got[1], want[1], rtol=1e-4)
 
 
+def test_api_matches_reference_golden_at_baseline_scale():
+    """2 x 2048 images (262,144 descriptors per level and set: 64 sort tiles per direction, 2048 row tiles of the tensor-core
+    projection) against the UNMODIFIED reference, run once in the build container (tests/golden/make_golden.py --swd-large;
+    fixture: 2 x 5 floats).  Same seeds, same minibatches, same numpy stream; tolerance north_star's 1e-4."""
+    import os
+
+    from blurred_gan_b200 import sliced_wasserstein as sw
+    from conftest import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "swd_large.npz"))
+    n, mb, seed_r, seed_f, np_seed = (int(v) for v in g["config"])
+    reals = uniform_pm1(seed_r, (n, 3, 128, 128))
+    fakes = (0.9 * uniform_pm1(seed_f, (n, 3, 128, 128))).astype(np.float32)
+    fakes[:, :, ::2] *= 0.8
+    np.random.seed(np_seed)
+    r0, r1 = _run_api(sw.API((3, 128, 128)), reals, fakes, mb, True)
+    np.testing.assert_array_equal(r0, g["api_reals"])
+    np.testing.assert_allclose(r1, g["api_fakes"], rtol=1e-4)
+
+
+def test_downscale_minibatch_values():
+    """sliced_wasserstein.py:55-61 against the reference's golden (uint8 input) and the oracle (float input, ties)."""
+    import os
+
+    from blurred_gan_b200 import sliced_wasserstein as sw
+    from conftest import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "swd_downscale.npz"))
+    x = g["x"]
+    xd = torch.from_numpy(x).cuda()
+    assert sw.downscale_minibatch(xd, 0) is xd
+    for lod in (1, 2, 3):
+        got = sw.downscale_minibatch(xd, lod)
+        assert got.dtype == torch.uint8 and got.is_cuda
+        np.testing.assert_array_equal(got.cpu().numpy(), g["lod%d" % lod])
+        np.testing.assert_array_equal(sw.downscale_minibatch(x, lod).cpu().numpy(), g["lod%d" % lod])  # numpy in, like the reference
+    # float input with exact .5 ties and values outside [0, 255]: round-half-to-even and the clip
+    xf = (np.random.RandomState(72).randint(-40, 600, size=(2, 3, 16, 16)) * 0.5).astype(np.float32)
+    for lod in (1, 2):
+        np.testing.assert_array_equal(sw.downscale_minibatch(_dev(xf), lod).cpu().numpy(), so.downscale_minibatch(xf, lod))
+
+
 def _dist_worker(rank, world, port, out_dir):
     import os
     import sys

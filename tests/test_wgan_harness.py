@@ -231,6 +231,46 @@ def test_celeba_step_on_gpu_matches_the_oracle_blur_step(monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("controller", ["linear", "decay"])
+def test_sigma_controllers_drive_the_device_blur_without_synchronising(controller):
+    """SURVEY 8f row N2 on the device: a controller (callbacks.py:45-62 / the driver's linear 23 -> 0 anneal) writes sigma
+    before every batch and the blur layer in front of the critic picks it up -- radius, kernel choice and taps -- with parity
+    at every step and without a single device synchronisation (sync debug mode raises on any)."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import GaussianBlur2D
+
+    gan = _mnist_gan(GaussianBlur2D(23.0), batch=4).cuda()
+    assert gan.std.device.type == "cpu"  # sigma lives in host memory (launch parameter), the nets on the GPU
+    steps = 6
+    if controller == "linear":
+        ctl = callbacks.LinearBlurSchedule(total_batches=steps, max_value=23.0, min_value=0.0)
+        want_std = [23.0 - 23.0 * i / (steps - 1) for i in range(steps)]
+    else:
+        ctl = callbacks.BlurDecayController(total_n_training_examples=20, max_value=8.0)  # decay_steps = 2 batches
+        want_std = [8.0 * 0.96 ** (i / 2.0) for i in range(steps)]
+    ctl.set_model(gan)
+    x = torch.from_numpy(np.ascontiguousarray(np.random.RandomState(5).rand(4, 128, 128, 3).astype(np.float32) * 2 - 1)).cuda()
+    x_host = x.cpu().numpy()
+    outs, paths = [], []
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        for i in range(steps):
+            gan.n_batches = i
+            ctl.on_batch_begin()
+            outs.append(gan.blur(x))  # what Sequential([blur, discriminator]) feeds the critic (blurred_gan.py:30-35)
+            paths.append(ops.last_blur_path())
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert len(set(paths)) > 1, "the anneal should cross kernel choices (tensor-core kernel for wide taps, direct kernel for few)"
+    for i, y in enumerate(outs):
+        assert float(gan.blur.std_value()) == pytest.approx(want_std[-1])
+        want = bo.blur_images_tf_ref(x_host, np.float32(want_std[i]))
+        err = np.abs(y.cpu().numpy() - want).max() / np.abs(want).max()
+        assert err <= 1e-5, "step %d (std %.4f): %.3g" % (i, want_std[i], err)
+
+
+@pytest.mark.gpu
 def test_swd_metric_on_device_tensors():
     from blurred_gan_b200.metrics import SWDMetric
 
