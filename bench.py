@@ -634,7 +634,9 @@ class _EventTimer:
         return len(self.pairs.get(name, []))
 
 
-# HBM bytes the radix sort moves per key (csrc/sort.cu): 4 digit passes x (scatter read + write) + the histogram reads
+# HBM bytes the radix sort moves per key (csrc/sort.cu): 4 digit passes x (histogram read + scatter read + write); in the
+# fused sort + |A - B| call the last pass over B reads the sorted A instead of writing (same count), and the separate
+# |A - B| pass (8 bytes per pair) no longer exists
 SORT_BYTES_PER_KEY = 48
 
 
@@ -684,7 +686,7 @@ def swd_timing(n_images, dev, rank=0, world=1, hbm_peak=None):
     run()  # warm-up (allocator, NCCL channels)
     res, t = run()
     # third run with CUDA-event pairs around the library calls: device time per phase (not part of eval_s)
-    for name in ("swd_sort_", "swd_project", "swd_absdiff_sum", "swd_normalise_", "swd_feed"):
+    for name in ("swd_sort_diff_", "swd_project", "swd_normalise_", "swd_feed"):
         timer.wrap(ops, name)
     timer.wrap(bd, "all_gather_rows")
     try:
@@ -708,13 +710,14 @@ def swd_timing(n_images, dev, rank=0, world=1, hbm_peak=None):
            "end_s": round(total_s - feed_s, 4), "images_per_s": round(2 * rounds * world * mb / total_s, 1),
            "result_x1e3": [float(v) for v in res],
            "device_time_s": {k: round(v, 4) for k, v in phases.items()}, "calls": calls,
-           "sort": {"keys_whole_job": keys_job, "keys_per_rank": keys_rank, "sort_s": round(phases["swd_sort_"], 4),
-                    "gkeys_per_s_per_gpu": round(keys_rank / max(phases["swd_sort_"], 1e-9) / 1e9, 2),
-                    "gkeys_per_s_whole_job": round(keys_job / max(phases["swd_sort_"], 1e-9) / 1e9, 2),
+           "sort": {"keys_whole_job": keys_job, "keys_per_rank": keys_rank, "sort_s": round(phases["swd_sort_diff_"], 4),
+                    "gkeys_per_s_per_gpu": round(keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9, 2),
+                    "gkeys_per_s_whole_job": round(keys_job / max(phases["swd_sort_diff_"], 1e-9) / 1e9, 2),
                     "hbm_bytes_per_key": SORT_BYTES_PER_KEY,
-                    "hbm_gbs": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_"], 1e-9) / 1e9, 1),
-                    "hbm_frac": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_"], 1e-9) / 1e9 / hbm_peak, 4) if hbm_peak else None},
-           "note": "host RNG draws (reference order) are inside eval_s; device_time_s: CUDA-event pairs around the calls in a separate run"}
+                    "hbm_gbs": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9, 1),
+                    "hbm_frac": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9 / hbm_peak, 4) if hbm_peak else None},
+           "note": "host RNG draws (reference order) are inside eval_s; device_time_s: CUDA-event pairs around the calls in a separate run; "
+                   "swd_sort_diff_ = both sorts + the fused |A - B| sums (bgan_swd_sort_diff_f32)"}
     if world > 1:
         ag = phases["all_gather_rows"]
         recv = desc_bytes_job * (world - 1) // world

@@ -501,6 +501,18 @@ bool geometry(int n, int c, int h, int w, int layout, Geometry* g) {
     return false;
 }
 
+// NHWC with C in 2 .. 4 whose channel planes qualify for the two-pass tensor-core kernel: planar copy + that kernel's scratch
+bool nhwc_via_planar_ok(const Geometry& g, int radius) {
+    if (g.ES < 2 || g.ES > 4) return false;
+    const int W = g.Wc / g.ES;
+    return static_cast<int64_t>(g.planes) * g.ES < (int64_t(1) << 31) && blur_axis_shape_ok(g.planes * g.ES, g.H, W, 1, radius);
+}
+size_t nhwc_via_planar_bytes(const Geometry& g) {
+    const size_t planar = (static_cast<size_t>(g.planes) * g.H * g.Wc * sizeof(float) + 255) & ~size_t(255);
+    return planar + blur_axis_workspace_bytes(g.planes * g.ES, g.H, g.Wc / g.ES);
+}
+
+
 }  // namespace
 }  // namespace bgan
 
@@ -548,6 +560,7 @@ extern "C" size_t bgan_blur2d_workspace_bytes(int n, int c, int height, int widt
     Geometry g;
     if (!geometry(n, c, height, width, layout, &g) || radius < 0) return 0;
     if (blur_axis_shape_ok(g.planes, g.H, g.Wc, g.ES, radius)) return blur_axis_workspace_bytes(g.planes, g.H, g.Wc);
+    if (nhwc_via_planar_ok(g, radius)) return nhwc_via_planar_bytes(g);
     Plan fused = choose_plan(g.H, g.Wc, g.ES, radius, radius);
     if (fused.ok) return 0;
     return static_cast<size_t>(g.planes) * g.H * g.Wc * sizeof(float);
@@ -581,6 +594,65 @@ __global__ void __launch_bounds__(256) lerp_rows_scalar_kernel(const float* __re
     }
 }
 
+// Layout conversion for large NHWC images (BASELINE configs[3] in the reference's own layout, gaussian_blur.py:111-130): the
+// two-pass tensor-core kernel needs planes that are contiguous along the blurred axis, and a channel-interleaved row cannot
+// be staged by TMA one channel at a time (12-byte element stride).  Interleaved <-> planar through shared memory, both sides
+// coalesced: chunk of kCvtPix consecutive pixels of one image per CTA iteration; the interleaved side moves as float4, the
+// smem side is read / written with stride C words across lanes (conflict-free for C = 3).
+constexpr int kCvtPix = 1024, kCvtThreads = 256;
+template <bool TO_PLANAR>
+__global__ void __launch_bounds__(kCvtThreads) layout_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t images,
+                                                                     int64_t hw, int C) {
+    __shared__ __align__(16) float s_buf[kCvtPix * 4];
+    const int64_t chunks_per_image = (hw + kCvtPix - 1) / kCvtPix;
+    const int64_t chunks = images * chunks_per_image;
+    for (int64_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const int64_t img = ch / chunks_per_image;
+        const int64_t p0 = (ch - img * chunks_per_image) * kCvtPix;
+        const int npix = static_cast<int>(hw - p0 < kCvtPix ? hw - p0 : kCvtPix);
+        const float* inter_c = (TO_PLANAR ? src : dst) + (img * hw + p0) * C;   // interleaved side of this chunk
+        const int nfl = npix * C;
+        const bool vec = (nfl & 3) == 0 && (reinterpret_cast<uintptr_t>(inter_c) & 15) == 0;
+        if (TO_PLANAR) {
+            if (vec) {
+                for (int i = threadIdx.x; i < nfl / 4; i += kCvtThreads)
+                    reinterpret_cast<float4*>(s_buf)[i] = __ldcs(reinterpret_cast<const float4*>(inter_c) + i);
+            } else {
+                for (int i = threadIdx.x; i < nfl; i += kCvtThreads) s_buf[i] = __ldcs(inter_c + i);
+            }
+            __syncthreads();
+            for (int c = 0; c < C; ++c) {
+                float* plane = dst + (img * C + c) * hw + p0;
+                for (int q = threadIdx.x; q < npix; q += kCvtThreads) plane[q] = s_buf[q * C + c];
+            }
+        } else {
+            for (int c = 0; c < C; ++c) {
+                const float* plane = src + (img * C + c) * hw + p0;
+                for (int q = threadIdx.x; q < npix; q += kCvtThreads) s_buf[q * C + c] = __ldcs(plane + q);
+            }
+            __syncthreads();
+            float* inter = dst + (img * hw + p0) * C;
+            if (vec) {
+                for (int i = threadIdx.x; i < nfl / 4; i += kCvtThreads) __stcs(reinterpret_cast<float4*>(inter) + i, reinterpret_cast<const float4*>(s_buf)[i]);
+            } else {
+                for (int i = threadIdx.x; i < nfl; i += kCvtThreads) inter[i] = s_buf[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int layout_convert(bool to_planar, const float* src, float* dst, int64_t images, int64_t hw, int C, cudaStream_t stream) {
+    const int64_t chunks = images * ((hw + kCvtPix - 1) / kCvtPix);
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(chunks, static_cast<int64_t>(device_sm_count()) * 8));
+    if (to_planar)
+        layout_convert_kernel<true><<<grid, kCvtThreads, 0, stream>>>(src, dst, images, hw, C);
+    else
+        layout_convert_kernel<false><<<grid, kCvtThreads, 0, stream>>>(src, dst, images, hw, C);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
 // One tensor (io.count == 1) or several equally shaped ones.  The 128 x 128 kernels take all tensors in one launch;
 // every other shape falls back to one launch sequence per tensor (same stream, so the scratch is reused).
 int blur2d_dispatch(const MultiIO& io, const Geometry& g, int rule, float std_eff, int radius, const float* taps_device, void* ws,
@@ -599,6 +671,30 @@ int blur2d_dispatch(const MultiIO& io, const Geometry& g, int rule, float std_ef
             if (rc) return rc;
         }
         return 0;
+    }
+    // large NHWC images: interleaved -> planar, the two tensor-core passes on the planes (in place in the planar copy: the
+    // second pass no longer reads it), planar -> interleaved.  Two extra HBM passes (0.25 ms at configs[3]) instead of the
+    // CUDA-core tile kernel's 770 FMAs per pixel (12.6 - 24.9 ms).
+    if (nhwc_via_planar_ok(g, radius) && ws != nullptr && ws_bytes >= nhwc_via_planar_bytes(g) && reinterpret_cast<uintptr_t>(ws) % 256 == 0) {
+        const int W = g.Wc / g.ES, planes = g.planes * g.ES;
+        const size_t planar_bytes = (static_cast<size_t>(g.planes) * g.H * g.Wc * sizeof(float) + 255) & ~size_t(255);
+        float* planar = static_cast<float*>(ws);
+        void* axis_ws = static_cast<char*>(ws) + planar_bytes;
+        bool aligned = true;
+        for (int t = 0; t < io.count; ++t)
+            aligned = aligned && reinterpret_cast<uintptr_t>(io.x[t]) % 16 == 0 && reinterpret_cast<uintptr_t>(io.y[t]) % 16 == 0;
+        if (aligned && blur_axis_eligible(planes, g.H, W, 1, radius, planar, planar)) {
+            g_last_path = 7;
+            for (int t = 0; t < io.count; ++t) {
+                int rc = layout_convert(true, io.x[t], planar, g.planes, static_cast<int64_t>(g.H) * W, g.ES, stream);
+                if (rc) return rc;
+                rc = blur_axis_launch(planar, planar, planes, g.H, W, rule, std_eff, radius, taps_device, axis_ws, ws_bytes - planar_bytes, stream);
+                if (rc) return rc;
+                rc = layout_convert(false, planar, io.y[t], g.planes, static_cast<int64_t>(g.H) * W, g.ES, stream);
+                if (rc) return rc;
+            }
+            return 0;
+        }
     }
     // the unit counters of the one-launch kernels are 32-bit
     const bool one_launch = static_cast<int64_t>(g.planes) * g.ES * io.count * 2 < (int64_t(1) << 31);

@@ -33,13 +33,16 @@ constexpr int kAxWarps = kAxThreads / 32;
 constexpr int kAxStoreWarps = 4;               // warps 17..20: epilogue (accumulators -> global), off the critical path
 constexpr int kAxCta = kAxThreads + 32 + 32 * kAxStoreWarps;  // + the MMA-issuing warp + the store warps
 constexpr int kAxMaxNb = 2;                    // radius <= 256
-constexpr uint32_t kALBO = 144, kASBO = 16 * kALBO, kATile = 16 * kASBO;  // padded K-major operand tile (see blur_tc.cu)
+// B operand (fp16 hi | lo of a 128 x 128 block of `in`): K-major tiles with the 128-byte hardware swizzle, as in
+// blur_tc.cu (two K-blocks of 64 elements; row r owns 128 contiguous bytes per K-block, 16-byte chunk c at c ^ (r % 8)).
+// Two sets, so that the conversion of block u + 1 overlaps the MMAs of block u.
+constexpr uint32_t kAKBlock = kB * 128;        // 16384: 128 rows x 64 K-elements
+constexpr uint32_t kATile = 2 * kAKBlock;      // 32768
 constexpr uint32_t kAStage = kB * kB * 4;      // 65536
-constexpr uint32_t kAOffStage = 0;             // two staging blocks
-constexpr uint32_t kAOffX1 = 2 * kAStage;      // X hi tile (the raw taps live here until the first conversion)
-constexpr uint32_t kAOffX2 = kAOffX1 + kATile;
+constexpr uint32_t kAOffStage = 0;             // one fp32 staging block (TMA destination)
+constexpr uint32_t kAOffX = kAStage;           // X[set][hi | lo]; the raw taps live here until the first conversion
 constexpr uint32_t kAStripBytes = 12288;       // (32 * 2 + 31) core matrices x 128 B = 12160
-constexpr uint32_t kAOffS1 = kAOffX2 + kATile;
+constexpr uint32_t kAOffS1 = kAOffX + 4 * kATile;
 constexpr uint32_t kAOffS2 = kAOffS1 + kAStripBytes;
 constexpr uint32_t kAOffMisc = kAOffS2 + kAStripBytes;  // s_scale[128], s_inv[128], barriers
 constexpr uint32_t kASmem = kAOffMisc + 1536 + 256;
@@ -59,11 +62,20 @@ struct AxisArgs {
     const float* taps_dev;
 };
 
-__device__ __forceinline__ uint32_t ax_tile_off(int row, int k) { return (row >> 3) * kASBO + (k >> 3) * kALBO + (row & 7) * 16 + (k & 7) * 2; }
+__device__ __forceinline__ uint32_t ax_tile_off(int row, int k) {
+    return (k >> 6) * kAKBlock + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
+}
+// A operand: the Toeplitz strip, no swizzle, LBO = SBO = 128 B
 __device__ __forceinline__ uint64_t ax_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) | (static_cast<uint64_t>(sbo >> 4) << 32) |
            (1ull << 46);
 }
+// B operand: SWIZZLE_128B K-major tile (LBO unused = 1, SBO = 1024, layout type 2)
+__device__ __forceinline__ uint64_t ax_desc_sw128(uint32_t saddr) {
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// descriptor increment (16-byte units) of K-step k: 16 elements = 32 bytes inside the swizzle atom, 4 steps per K-block
+__device__ __forceinline__ constexpr uint64_t ax_kstep(int k) { return static_cast<uint64_t>((k >> 2) * (kAKBlock >> 4) + (k & 3) * 2); }
 __device__ __forceinline__ void ax_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -136,13 +148,50 @@ __device__ __forceinline__ TileCoord tile_coord(const AxisArgs& a, int tile) {
     return c;
 }
 
+// K-steps (16 inputs k each) of block l = d + nb that the band |k - j| <= r of a 128-output tile touches: the centre block
+// entirely, a block to the left only its last columns (k_local >= 128 |d| - r), a block to the right only its first ones
+// (k_local <= r - 1 - 128 (d - 1)).  Everything else multiplies zeros of T and is neither converted nor issued.
+__device__ __forceinline__ void ks_range(int l, int nb, int radius, int& k0, int& k1) {
+    const int d = l - nb;
+    k0 = 0;
+    k1 = 7;
+    if (d < 0) k0 = max(0, -d * kB - radius) >> 4;
+    if (d > 0) k1 = min(7, (radius - 1 - (d - 1) * kB) >> 4);
+}
+
+// walks the (tile, block) sequence of one CTA
+struct BlockCursor {
+    int tile, l;
+    TileCoord c;
+    __device__ __forceinline__ void init(const AxisArgs& a, int first, int n_tiles) {
+        tile = first;
+        c = tile_coord(a, min(tile, n_tiles - 1));
+        l = c.l0;
+    }
+    __device__ __forceinline__ void advance(const AxisArgs& a, int stride, int n_tiles) {
+        if (++l > c.l1) {
+            tile += stride;
+            if (tile < n_tiles) {
+                c = tile_coord(a, tile);
+                l = c.l0;
+            }
+        }
+    }
+};
+
+// Pipeline (per CTA, blocks numbered u = 0, 1, ... in (tile, l) order):
+//   TMA           block u + 1 -> staging (one buffer), issued as soon as block u has been read into registers; block u + 2 is
+//                 pulled into L2 at the same time, so the load that follows finds it there
+//   compute warps staging(u) -> registers -> fp16 hi | lo tiles X[u & 1]   (only the K-steps the band touches)
+//   MMA warp      block u from X[u & 1] while the compute warps convert block u + 1 into the other set
+//   store warps   accumulator pair of tile n - 1 -> global while tile n accumulates into the other pair
 __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* s_g = reinterpret_cast<float*>(smem + kAOffX1);  // taps (<= 513), only until the strip is built
+    float* s_g = reinterpret_cast<float*>(smem + kAOffX);  // taps (<= 513), only until the strip is built
     float* s_scale = reinterpret_cast<float*>(smem + kAOffMisc);  // [128] per input row of the tile being converted
     float* s_inv = s_scale + kB;                                  // [2][128]: tile parity (read by the store warps one tile later)
-    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kAOffMisc + 1536);  // [2]
-    uint64_t* mbar_mma = mbar_tma + 2;       // one phase per block: its MMAs are complete (X tiles free)
+    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kAOffMisc + 1536);  // one phase per block
+    uint64_t* mbar_mma = mbar_tma + 1;       // [2]: the MMAs reading X[set] are complete (the set may be rewritten)
     uint64_t* mbar_acc_full = mbar_tma + 3;  // [2]: all MMAs of a tile complete, accumulator pair valid
     uint64_t* mbar_acc_free = mbar_tma + 5;  // [2]: the store warps hold the accumulator pair in registers
     double* s_red = reinterpret_cast<double*>(mbar_tma + 7);
@@ -156,9 +205,9 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         tma_prefetch_desc(&tmap);
-        mbar_init(mbar_tma + 0, 1);
-        mbar_init(mbar_tma + 1, 1);
-        mbar_init(mbar_mma, 1);
+        mbar_init(mbar_tma, 1);
+        mbar_init(mbar_mma + 0, 1);
+        mbar_init(mbar_mma + 1, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(mbar_acc_full + b, 1);
             mbar_init(mbar_acc_free + b, kAxStoreWarps);
@@ -193,7 +242,6 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
     const int jl = ((warp & 3) * 32 + lane) ^ kARev;  // output position held by this thread's accumulator row
     asm volatile("griddepcontrol.wait;" ::: "memory");  // `in` may be written, `out` may still be read by the previous grid
 
-    // Blocks are numbered u = 0, 1, ... in the order (tile, l); block u uses staging[u & 1] and phase u of mbar_mma.
     if (warp == kAxWarps) {
         // ================= MMA issuer =================================================================
         int u = 0, n = 0;
@@ -201,20 +249,24 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
             const TileCoord c = tile_coord(a, tile);
             const uint32_t d_main = tmem + (n & 1) * 256, d_cross = d_main + 128;
             for (int l = c.l0; l <= c.l1; ++l, ++u) {
-                named_bar_sync(1, kAxThreads + 32);  // X tiles of block u written
+                named_bar_sync(1 + (u & 1), kAxThreads + 32);  // X[u & 1] of block u written
                 if (lane == 0) {
                     if (l == c.l0 && n >= 2) mbar_wait(mbar_acc_free + (n & 1), ((n - 2) >> 1) & 1);  // accumulator pair drained
                     ax_fence_after();
+                    int k0, k1;
+                    ks_range(l, a.nb, a.radius, k0, k1);
                     const uint64_t a1 = ax_desc(sbase + kAOffS1 + l * 16 * 128, 128, 128), a2 = ax_desc(sbase + kAOffS2 + l * 16 * 128, 128, 128);
-                    const uint64_t b1 = ax_desc(sbase + kAOffX1, kALBO, kASBO), b2 = ax_desc(sbase + kAOffX2, kALBO, kASBO);
+                    const uint32_t xb = sbase + kAOffX + (u & 1) * 2 * kATile;
+                    const uint64_t b1 = ax_desc_sw128(xb), b2 = ax_desc_sw128(xb + kATile);
                     const uint32_t acc0 = l > c.l0;  // the first block of a tile overwrites the accumulators
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) ax_mma(d_cross, a1 + k * 16, b2 + k * 18, acc0 | (k > 0));
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) ax_mma(d_cross, a2 + k * 16, b1 + k * 18, 1);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) ax_mma(d_main, a1 + k * 16, b1 + k * 18, acc0 | (k > 0));
-                    ax_commit(mbar_mma);
+                    // cross and main products alternate: two independent accumulators
+                    for (int k = k0; k <= k1; ++k) {
+                        const uint32_t acc = acc0 | (k > k0);
+                        ax_mma(d_cross, a1 + k * 16, b2 + ax_kstep(k), acc);
+                        ax_mma(d_main, a1 + k * 16, b1 + ax_kstep(k), acc);
+                        ax_mma(d_cross, a2 + k * 16, b1 + ax_kstep(k), 1);
+                    }
+                    ax_commit(mbar_mma + (u & 1));
                     if (l == c.l1) ax_commit(mbar_acc_full + (n & 1));
                 }
                 __syncwarp();
@@ -261,28 +313,26 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
         }
     } else {
         // ================= compute warps ==============================================================
-        // load cursor (thread 0): the next block to request, two blocks ahead of the one being converted
-        int ld_tile = first, ld_l = 0, ld_u = 0;
-        TileCoord ld_c = tile_coord(a, min(ld_tile, n_tiles - 1));
-        ld_l = ld_c.l0;
-        auto issue_next_load = [&]() {
-            if (ld_tile >= n_tiles) return;
-            mbar_arrive_expect_tx(mbar_tma + (ld_u & 1), kAStage);
-            tma_load_3d(smem + kAOffStage + (ld_u & 1) * kAStage, &tmap, mbar_tma + (ld_u & 1), (ld_c.jb + ld_l - a.nb) * kB, ld_c.ib * kB,
-                        ld_c.plane);
-            ++ld_u;
-            if (++ld_l > ld_c.l1) {
-                ld_tile += stride;
-                if (ld_tile < n_tiles) {
-                    ld_c = tile_coord(a, ld_tile);
-                    ld_l = ld_c.l0;
-                }
-            }
+        BlockCursor ld, pf;  // thread 0: next block to load into staging / to pull into L2 (one block further ahead)
+        ld.init(a, first, n_tiles);
+        pf.init(a, first, n_tiles);
+        auto issue_load = [&]() {
+            if (ld.tile >= n_tiles) return;
+            mbar_arrive_expect_tx(mbar_tma, kAStage);
+            tma_load_3d(smem + kAOffStage, &tmap, mbar_tma, (ld.c.jb + ld.l - a.nb) * kB, ld.c.ib * kB, ld.c.plane);
+            ld.advance(a, stride, n_tiles);
+        };
+        auto issue_prefetch = [&]() {
+            if (pf.tile >= n_tiles) return;
+            tma_prefetch_l2_3d(&tmap, (pf.c.jb + pf.l - a.nb) * kB, pf.c.ib * kB, pf.c.plane);
+            pf.advance(a, stride, n_tiles);
         };
         if (tid == 0) {
-            issue_next_load();
-            issue_next_load();
+            issue_load();                        // block 0
+            issue_prefetch();                    // (block 0: already on its way)
+            issue_prefetch();                    // block 1 -> L2
         }
+        const float* stage = reinterpret_cast<const float*>(smem + kAOffStage);
         int u = 0, n = 0;
         for (int tile = first; tile < n_tiles; tile += stride, ++n) {
             const TileCoord c = tile_coord(a, tile);
@@ -297,33 +347,54 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
                 s_scale[tid] = __int_as_float((266 - eb) << 23);  // max |row| -> [2^12, 2^13)
                 s_inv[(n & 1) * kB + tid] = __int_as_float((eb - 12) << 23);
             }
-            named_bar_sync(2, kAxThreads);
+            named_bar_sync(3, kAxThreads);
             for (int l = c.l0; l <= c.l1; ++l, ++u) {
-                // ---- staging -> registers ----
-                mbar_wait(mbar_tma + (u & 1), (u >> 1) & 1);
-                const float* stage = reinterpret_cast<const float*>(smem + kAOffStage + (u & 1) * kAStage);
+                int k0, k1;
+                ks_range(l, a.nb, a.radius, k0, k1);
+                const int nks = k1 - k0 + 1;      // K-steps of this block that are needed: 16 nks columns from column 16 k0
+                const int f4_row = 4 * nks;       // float4 per row
+                // ---- staging -> registers (thread handles float4 g = q * 512 + tid, q < nks: row g / f4_row) ----
+                mbar_wait(mbar_tma, u & 1);
                 float4 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(stage + (q * kAxThreads + tid) * 4);
-                named_bar_sync(2, kAxThreads);  // staging drained
-                if (tid == 0) issue_next_load();
-                if (u > 0) mbar_wait(mbar_mma, (u - 1) & 1);  // MMAs of the previous block complete: X tiles free
-                // ---- registers -> X hi | lo tiles (row = i, K = k) ----
+                auto locate = [&](int q, int& h, int& w) {  // (recomputed in the second loop rather than kept in registers)
+                    const int g = q * kAxThreads + tid;
+                    h = nks == 8 ? (g >> 5) : g / f4_row;
+                    w = 16 * k0 + ((g - h * f4_row) << 2);
+                };
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int f = q * kAxThreads + tid;
-                    const int h = f >> 5, w = (f & 31) << 2;
-                    const float sc = s_scale[h];
-                    __half2 hi[2], lo[2];
-                    ax_split2(v[q].x * sc, v[q].y * sc, hi[0], lo[0]);
-                    ax_split2(v[q].z * sc, v[q].w * sc, hi[1], lo[1]);
-                    const uint32_t off = ax_tile_off(h, w);
-                    *reinterpret_cast<uint2*>(smem + kAOffX1 + off) = *reinterpret_cast<uint2*>(hi);
-                    *reinterpret_cast<uint2*>(smem + kAOffX2 + off) = *reinterpret_cast<uint2*>(lo);
+                    if (q < nks) {
+                        int h, w;
+                        locate(q, h, w);
+                        v[q] = *reinterpret_cast<const float4*>(stage + h * kB + w);
+                    }
+                }
+                named_bar_sync(3, kAxThreads);  // staging drained
+                if (tid == 0) {
+                    issue_load();       // block u + 1 (in L2 already)
+                    issue_prefetch();   // block u + 2 -> L2
+                }
+                if (u >= 2) mbar_wait(mbar_mma + (u & 1), ((u - 2) >> 1) & 1);  // MMAs of block u - 2 complete: X[u & 1] free
+                // ---- registers -> X[u & 1] hi | lo tiles (row = i, K = k) ----
+                unsigned char* x1 = smem + kAOffX + (u & 1) * 2 * kATile;
+                unsigned char* x2 = x1 + kATile;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q < nks) {
+                        int h, w;
+                        locate(q, h, w);
+                        const float sc = s_scale[h];
+                        __half2 hi[2], lo[2];
+                        ax_split2(v[q].x * sc, v[q].y * sc, hi[0], lo[0]);
+                        ax_split2(v[q].z * sc, v[q].w * sc, hi[1], lo[1]);
+                        const uint32_t off = ax_tile_off(h, w);
+                        *reinterpret_cast<uint2*>(x1 + off) = *reinterpret_cast<uint2*>(hi);
+                        *reinterpret_cast<uint2*>(x2 + off) = *reinterpret_cast<uint2*>(lo);
+                    }
                 }
                 fence_proxy_async();
                 ax_fence_before();
-                named_bar_sync(1, kAxThreads + 32);  // -> MMAs of block u
+                named_bar_arrive(1 + (u & 1), kAxThreads + 32);  // -> MMAs of block u
             }
         }
     }

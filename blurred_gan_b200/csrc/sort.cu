@@ -37,19 +37,35 @@ __device__ __forceinline__ uint32_t load_key(const uint32_t* __restrict__ p) {
 // MATCH: one match_any -- fast when a 32-key row holds a handful of distinct digits (the top byte of the keys: sign and
 // exponent), but its cost grows with the number of distinct values (measured: ~240 cycles per row for uniform digits).
 // Otherwise eight ballots, one per digit bit: constant time.
-template <bool MATCH>
+// One digit bit: peers &= lanes whose bit equals mine.  Written as PTX so that it stays four instructions (test, vote and
+// two predicated logic operations); the C++ form `peers &= bit ? m : ~m` compiled to six or seven per bit, and the ranking
+// loop is what bounds the scatter kernel (instruction-bound: profiles/r01e_swd.md).
+#define BGAN_MATCH_BIT(B)                                  \
+    "and.b32 t, %1, " #B ";\n\t"                           \
+    "setp.ne.u32 p, t, 0;\n\t"                             \
+    "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"           \
+    "@!p not.b32 m, m;\n\t"                                \
+    "and.b32 %0, %0, m;\n\t"
+
+template <bool MATCH, bool PADDED>
 __device__ __forceinline__ uint32_t same_digit_lanes(uint32_t d) {
     if constexpr (MATCH) {
         return __match_any_sync(0xffffffffu, d);
     } else {
-        uint32_t peers = __ballot_sync(0xffffffffu, d < 256u);
-        if (d >= 256u) peers = ~peers;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t m = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? m : ~m;
+        uint32_t peers;
+        if constexpr (PADDED) {
+            peers = __ballot_sync(0xffffffffu, d < 256u);
+            if (d >= 256u) peers = ~peers;
+        } else {
+            peers = 0xffffffffu;
         }
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 m, t;\n\t" BGAN_MATCH_BIT(1) BGAN_MATCH_BIT(2) BGAN_MATCH_BIT(4) BGAN_MATCH_BIT(8) BGAN_MATCH_BIT(16) BGAN_MATCH_BIT(32)
+                BGAN_MATCH_BIT(64) BGAN_MATCH_BIT(128) "}"
+            : "+r"(peers)
+            : "r"(d));
         return peers;
     }
 }
@@ -161,11 +177,24 @@ struct ScatterSmem {
     uint32_t gdelta[kRadix];           // global position of the tile's first key of a digit - its first local slot
     uint32_t keys[kTile];
     uint32_t scan[kSortWarps];
+    double diff[kSortWarps];
 };
 
-template <bool FIRST, bool LAST, bool FULL, bool MATCH>
+// The |a - b| partial sums of the fused last pass go to kDiffSlots accumulators per sum (tile % kDiffSlots), added up by a
+// one-CTA kernel afterwards: tiles x segments fp64 atomics on a handful of addresses would serialise in L2.
+constexpr int kDiffSlots = 64;
+struct DiffArgs {
+    const float* ref;     // sorted reference segments (same layout as the keys), or nullptr
+    double* partial;      // [sums][kDiffSlots]
+    int seg_offset;       // sum index of segment s = (s + seg_offset) / segs_per_sum
+    int segs_per_sum;
+};
+
+// DIFF (only with LAST): the keys are not written; every key meets the element of `ref` that sits at its final position
+// and sum |ref - key| is accumulated instead (sliced_wasserstein.py:47-50: sort both projections, mean |A - B|).
+template <bool FIRST, bool LAST, bool FULL, bool MATCH, bool DIFF>
 __device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
-                                             int64_t rows, int tiles, int shift, const uint32_t* __restrict__ offsets) {
+                                             int64_t rows, int tiles, int shift, const uint32_t* __restrict__ offsets, const DiffArgs& da) {
     auto& s_cnt = sm.cnt;
     auto& s_gdelta = sm.gdelta;
     auto& s_keys = sm.keys;
@@ -197,7 +226,7 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __
         const bool ok = FULL || warp_base + i * 32 + lane < valid;
         // lanes holding padding keys vote with digit 256 so that they never disturb a real digit
         const uint32_t d = ok ? (key[i] >> shift) & 0xff : 256u;
-        const uint32_t peers = same_digit_lanes<MATCH>(d);
+        const uint32_t peers = same_digit_lanes<MATCH, !FULL>(d);
         const int leader = __ffs(peers) - 1;
         // the lowest lane of every group bumps the warp's counter of that digit (groups hold different digits, so plain
         // read + write; the __syncwarp makes it visible to whichever lane leads that digit in the next row)
@@ -250,26 +279,64 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __
     __syncthreads();
 
     // runs of consecutive addresses out to global
+    if constexpr (DIFF) {
+        const float* ref = da.ref + static_cast<size_t>(seg) * rows;
+        uint32_t kk[kItems];
+        float rr[kItems];
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
-        const int slot = i * kSortThreads + tid;
-        if (FULL || slot < valid) {
-            const uint32_t k = s_keys[slot];
-            dst[s_gdelta[(k >> shift) & 0xff] + slot] = LAST ? ordered_to_float(k) : k;
+        for (int i = 0; i < kItems; ++i) {
+            const int slot = i * kSortThreads + tid;
+            const bool ok = FULL || slot < valid;
+            kk[i] = ok ? s_keys[slot] : 0u;
+            rr[i] = ok ? __ldg(ref + s_gdelta[(kk[i] >> shift) & 0xff] + slot) : 0.0f;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int slot = i * kSortThreads + tid;
+            if (FULL || slot < valid) acc += static_cast<double>(fabsf(rr[i] - __uint_as_float(ordered_to_float(kk[i]))));
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sm.diff[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) t += sm.diff[w];
+            atomicAdd(da.partial + static_cast<size_t>((seg + da.seg_offset) / da.segs_per_sum) * kDiffSlots + (tile % kDiffSlots), t);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int slot = i * kSortThreads + tid;
+            if (FULL || slot < valid) {
+                const uint32_t k = s_keys[slot];
+                dst[s_gdelta[(k >> shift) & 0xff] + slot] = LAST ? ordered_to_float(k) : k;
+            }
         }
     }
 }
 
-template <bool FIRST, bool LAST, bool MATCH>
+template <bool FIRST, bool LAST, bool MATCH, bool DIFF>
 __global__ void __launch_bounds__(kSortThreads, 4) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, uint32_t* __restrict__ keys_out,
                                                                      int64_t rows, int tiles, int shift,
-                                                                     const uint32_t* __restrict__ offsets) {
+                                                                     const uint32_t* __restrict__ offsets, const DiffArgs da) {
     __shared__ ScatterSmem sm;
     // complete tiles run without any bounds logic; only the last tile of a segment can be ragged
     if ((static_cast<int64_t>(blockIdx.x) + 1) * kTile <= rows)
-        scatter_tile<FIRST, LAST, true, MATCH>(sm, keys_in, keys_out, rows, tiles, shift, offsets);
+        scatter_tile<FIRST, LAST, true, MATCH, DIFF>(sm, keys_in, keys_out, rows, tiles, shift, offsets, da);
     else
-        scatter_tile<FIRST, LAST, false, MATCH>(sm, keys_in, keys_out, rows, tiles, shift, offsets);
+        scatter_tile<FIRST, LAST, false, MATCH, DIFF>(sm, keys_in, keys_out, rows, tiles, shift, offsets, da);
+}
+
+// sums[s] += the kDiffSlots partial sums of sum s (one warp per sum)
+__global__ void diff_finish_kernel(const double* __restrict__ partial, int n_sums, double* __restrict__ sums) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= n_sums) return;
+    double t = 0.0;
+    for (int i = lane; i < kDiffSlots; i += 32) t += partial[static_cast<size_t>(s) * kDiffSlots + i];
+    t = warp_sum(t);
+    if (lane == 0) sums[s] += t;
 }
 
 }  // namespace
@@ -290,13 +357,9 @@ extern "C" size_t bgan_swd_sort_workspace_bytes(int64_t rows, int segments) {
     return ((keys + 255) & ~size_t(255)) + 2 * counts + part;  // keys | counts | offsets | chunk partials
 }
 
-extern "C" int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws, size_t ws_bytes, void* stream_) {
-    BGAN_REQUIRE(keys_device && rows > 0 && segments > 0, BGAN_E_BADARG, "bgan_swd_sort_f32: bad arguments");
-    BGAN_REQUIRE(rows < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_swd_sort_f32: at most 2^31-1 rows per segment");
-    BGAN_REQUIRE(segments <= 65535, BGAN_E_BADARG, "bgan_swd_sort_f32: at most 65535 segments per call");
-    BGAN_REQUIRE(ws && ws_bytes >= bgan_swd_sort_workspace_bytes(rows, segments), BGAN_E_WORKSPACE,
-                 "bgan_swd_sort_f32: workspace of %zu bytes required, got %zu", bgan_swd_sort_workspace_bytes(rows, segments), ws_bytes);
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// The four passes over `segments` runs of `rows` keys at keys_device; with `da.ref` the last pass does not write the keys
+// but accumulates sum |ref - key| (see DiffArgs).
+static int sort_passes(float* keys_device, int64_t rows, int segments, void* ws, cudaStream_t stream, const DiffArgs& da) {
     const int tiles = static_cast<int>(ceil_div64(rows, kTile));
     const size_t keys_bytes = (static_cast<size_t>(rows) * segments * sizeof(uint32_t) + 255) & ~size_t(255);
     uint32_t* a = reinterpret_cast<uint32_t*>(keys_device);
@@ -311,23 +374,65 @@ extern "C" int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments,
         radix_scan_offsets_kernel<<<scan_grid, kRadix, 0, stream>>>(counts, tiles, chunks, part, offsets);
     };
     dim3 grid(tiles, segments);
+    const DiffArgs none{nullptr, nullptr, 0, 1};
 
     // pass 0: a -> b (float -> ordered uint on load)
     radix_hist_kernel<true, false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 0, counts);
     scan();
-    radix_scatter_kernel<true, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 0, offsets);
+    radix_scatter_kernel<true, false, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 0, offsets, none);
     // pass 1: b -> a
     radix_hist_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 8, counts);
     scan();
-    radix_scatter_kernel<false, false, false><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 8, offsets);
+    radix_scatter_kernel<false, false, false, false><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 8, offsets, none);
     // pass 2: a -> b
     radix_hist_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 16, counts);
     scan();
-    radix_scatter_kernel<false, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 16, offsets);
-    // pass 3: b -> a (ordered uint -> float on store)
+    radix_scatter_kernel<false, false, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 16, offsets, none);
+    // pass 3: b -> a (ordered uint -> float on store), or b -> sum |ref - key|
     radix_hist_kernel<false, true><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 24, counts);
     scan();
-    radix_scatter_kernel<false, true, true><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 24, offsets);
+    if (da.ref != nullptr)
+        radix_scatter_kernel<false, true, true, true><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 24, offsets, da);
+    else
+        radix_scatter_kernel<false, true, true, false><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 24, offsets, none);
+    BGAN_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws, size_t ws_bytes, void* stream_) {
+    BGAN_REQUIRE(keys_device && rows > 0 && segments > 0, BGAN_E_BADARG, "bgan_swd_sort_f32: bad arguments");
+    BGAN_REQUIRE(rows < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_swd_sort_f32: at most 2^31-1 rows per segment");
+    BGAN_REQUIRE(segments <= 65535, BGAN_E_BADARG, "bgan_swd_sort_f32: at most 65535 segments per call");
+    BGAN_REQUIRE(ws && ws_bytes >= bgan_swd_sort_workspace_bytes(rows, segments), BGAN_E_WORKSPACE,
+                 "bgan_swd_sort_f32: workspace of %zu bytes required, got %zu", bgan_swd_sort_workspace_bytes(rows, segments), ws_bytes);
+    return sort_passes(keys_device, rows, segments, ws, static_cast<cudaStream_t>(stream_), DiffArgs{nullptr, nullptr, 0, 1});
+}
+
+static size_t diff_partial_bytes(int n_sums) { return static_cast<size_t>(n_sums) * kDiffSlots * sizeof(double); }
+
+extern "C" size_t bgan_swd_sort_diff_workspace_bytes(int64_t rows, int segments, int n_sums) {
+    if (rows <= 0 || segments <= 0 || n_sums <= 0) return 0;
+    return ((bgan_swd_sort_workspace_bytes(rows, segments) + 255) & ~size_t(255)) + diff_partial_bytes(n_sums);
+}
+
+extern "C" int bgan_swd_sort_diff_f32(float* a_device, float* b_device, int64_t rows, int segments, int seg_offset, int segs_per_sum, int n_sums,
+                                      double* sums_device, void* ws, size_t ws_bytes, void* stream_) {
+    BGAN_REQUIRE(a_device && b_device && sums_device && rows > 0 && segments > 0, BGAN_E_BADARG, "bgan_swd_sort_diff_f32: bad arguments");
+    BGAN_REQUIRE(rows < (int64_t(1) << 31) && segments <= 65535, BGAN_E_BADARG, "bgan_swd_sort_diff_f32: at most 2^31-1 rows, 65535 segments");
+    BGAN_REQUIRE(seg_offset >= 0 && segs_per_sum > 0 && n_sums > 0 && (seg_offset + segments - 1) / segs_per_sum < n_sums, BGAN_E_BADARG,
+                 "bgan_swd_sort_diff_f32: segments %d .. %d do not map into %d sums of %d segments", seg_offset, seg_offset + segments - 1, n_sums,
+                 segs_per_sum);
+    BGAN_REQUIRE(ws && ws_bytes >= bgan_swd_sort_diff_workspace_bytes(rows, segments, n_sums), BGAN_E_WORKSPACE,
+                 "bgan_swd_sort_diff_f32: workspace of %zu bytes required, got %zu", bgan_swd_sort_diff_workspace_bytes(rows, segments, n_sums),
+                 ws_bytes);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double* partial = reinterpret_cast<double*>(static_cast<char*>(ws) + ((bgan_swd_sort_workspace_bytes(rows, segments) + 255) & ~size_t(255)));
+    int rc = sort_passes(a_device, rows, segments, ws, stream, DiffArgs{nullptr, nullptr, 0, 1});  // A: sorted in place
+    if (rc) return rc;
+    BGAN_CUDA_OK(cudaMemsetAsync(partial, 0, diff_partial_bytes(n_sums), stream));
+    rc = sort_passes(b_device, rows, segments, ws, stream, DiffArgs{a_device, partial, seg_offset, segs_per_sum});  // B: three passes, then the diff
+    if (rc) return rc;
+    diff_finish_kernel<<<ceil_div(n_sums, 4), 128, 0, stream>>>(partial, n_sums, sums_device);
     BGAN_LAUNCH_OK();
     return 0;
 }

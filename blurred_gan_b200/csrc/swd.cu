@@ -95,10 +95,13 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(const float* __restrict__ x
 
 // desc[m, c, i, j] = level[m / per_image, c, py[m] + j - half, px[m] + i - half]; per-channel sum / sum-of-squares.
 // One warp per descriptor (grid-stride): the lanes walk the C * nhood^2 floats of the descriptor, so the output row is
-// written coalesced and all index arithmetic is 32-bit.  The channel statistics are accumulated in fp64 per thread,
-// reduced per warp and per CTA in shared memory, and only then added to the global sums: six atomics per CTA (one atomic
-// per warp and statistic made this kernel 75 us per minibatch, all of it contention on six addresses).
-template <int MAXC>
+// written coalesced.  The descriptor geometry does not depend on the descriptor: every lane computes the image offsets and
+// channels of its <= kSlots elements once (the divisions by nhood^2 and nhood leave the loop), and the positions of a
+// warp's next descriptor are loaded while the current one is gathered.  The channel statistics are accumulated in fp64
+// per element slot, folded per channel at the end, reduced per warp and per CTA in shared memory, and only then added to
+// the global sums: six atomics per CTA on a grid of at most two CTAs per SM (one atomic per warp and statistic made this
+// kernel 75 us per minibatch; 1024 CTAs x 6 atomics on six addresses still 12.8 us, most of it the serialised L2 atomics).
+template <int MAXC, int SLOTS>
 __global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ level, int C, int h, int w, const int32_t* __restrict__ px,
                                                       const int32_t* __restrict__ py, int per_image, int nhood, int64_t n_desc,
                                                       float* __restrict__ out, double* __restrict__ sums) {
@@ -107,31 +110,56 @@ __global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ 
     const int per_chan = nhood * nhood;
     const int dlen = C * per_chan;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    double s1[MAXC], s2[MAXC];
+    int rel[SLOTS], chan[SLOTS];  // element k = lane + 32 t: offset from the patch origin, channel (-1: past the end)
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) s1[c] = s2[c] = 0.0;
-    for (int64_t m = static_cast<int64_t>(blockIdx.x) * warps + warp; m < n_desc; m += static_cast<int64_t>(gridDim.x) * warps) {
-        const int y0 = __ldg(py + m) - half, x0 = __ldg(px + m) - half;
-        const float* img = level + (m / per_image) * C * static_cast<int64_t>(h) * w;
-        float* dst = out + m * dlen;
-        for (int k = lane; k < dlen; k += 32) {
-            const int c = k / per_chan;
-            const int ij = k - c * per_chan;
-            const int i = ij / nhood, j = ij - i * nhood;
-            const float v = __ldg(img + (c * h + y0 + j) * w + x0 + i);
-            dst[k] = v;
-            const double dv = static_cast<double>(v);
+    for (int t = 0; t < SLOTS; ++t) {
+        const int k = lane + 32 * t;
+        const int c = k / per_chan;
+        const int ij = k - c * per_chan;
+        const int i = ij / nhood, j = ij - i * nhood;
+        chan[t] = k < dlen ? c : -1;
+        rel[t] = (c * h + j) * w + i;
+    }
+    double a1[SLOTS], a2[SLOTS];
 #pragma unroll
-            for (int cc = 0; cc < MAXC; ++cc)
-                if (cc == c) {
-                    s1[cc] += dv;
-                    s2[cc] += dv * dv;
-                }
+    for (int t = 0; t < SLOTS; ++t) a1[t] = a2[t] = 0.0;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * warps;
+    int64_t m = static_cast<int64_t>(blockIdx.x) * warps + warp;
+    int y_next = 0, x_next = 0;
+    if (m < n_desc) {
+        y_next = __ldg(py + m);
+        x_next = __ldg(px + m);
+    }
+    const int64_t image_stride = static_cast<int64_t>(C) * h * w;
+    for (; m < n_desc; m += step) {
+        const int y0 = y_next - half, x0 = x_next - half;
+        if (m + step < n_desc) {
+            y_next = __ldg(py + m + step);
+            x_next = __ldg(px + m + step);
+        }
+        const float* patch = level + (m / per_image) * image_stride + y0 * w + x0;
+        float* dst = out + m * dlen + lane;
+        float v[SLOTS];
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) v[t] = chan[t] >= 0 ? __ldg(patch + rel[t]) : 0.0f;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t) {
+            if (chan[t] >= 0) dst[32 * t] = v[t];
+            const double dv = static_cast<double>(v[t]);
+            a1[t] += dv;
+            a2[t] = fma(dv, dv, a2[t]);
         }
     }
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
-        const double a = warp_sum(s1[c]), b = warp_sum(s2[c]);
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int t = 0; t < SLOTS; ++t)
+            if (chan[t] == c) {
+                s1 += a1[t];
+                s2 += a2[t];
+            }
+        const double a = warp_sum(s1), b = warp_sum(s2);
         if (lane == 0) {
             s_part[warp][c] = a;
             s_part[warp][MAXC + c] = b;
@@ -148,9 +176,12 @@ __global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ 
     }
 }
 
-// desc = (desc - mean_c) / std_c, two fp32 operations like numpy's in-place `-=` then `/=`
-__global__ void normalise_kernel(float* __restrict__ desc, int64_t total, int C, int per_chan, const double* __restrict__ sums,
-                                 double count) {
+// desc = (desc - mean_c) / std_c, two fp32 operations like numpy's in-place `-=` then `/=` (a true IEEE division).
+// 128-bit accesses over the flat array, kNormUnroll of them in flight per thread; the position inside the descriptor
+// (which decides the channel) advances by a constant per grid stride, so there is no per-element division or modulo.
+constexpr int kNormUnroll = 4;
+__global__ void __launch_bounds__(256) normalise_kernel(float* __restrict__ desc, int64_t total, int C, int per_chan,
+                                                        const double* __restrict__ sums, double count) {
     __shared__ float s_mean[8], s_std[8];
     if (threadIdx.x < C) {
         const double mean = sums[threadIdx.x] / count;
@@ -160,11 +191,46 @@ __global__ void normalise_kernel(float* __restrict__ desc, int64_t total, int C,
     }
     __syncthreads();
     const int dlen = C * per_chan;
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(idx % dlen) / per_chan;
-        desc[idx] = (desc[idx] - s_mean[c]) / s_std[c];
+    auto apply = [&](float v, int e) {  // e: position inside the descriptor, 0 .. dlen - 1
+        int c = 0;
+        for (int b = per_chan; b <= e; b += per_chan) ++c;
+        return (v - s_mean[c]) / s_std[c];
+    };
+    const int64_t n4 = total >> 2;
+    const int64_t threads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t t0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    float4* d4 = reinterpret_cast<float4*>(desc);
+    int e = static_cast<int>((4 * t0) % dlen);                    // position of this thread's first element
+    const int de = static_cast<int>((4 * threads) % dlen);        // advance per grid stride
+    for (int64_t i = t0; i < n4; i += kNormUnroll * threads) {
+        float4 v[kNormUnroll];
+        int pos[kNormUnroll];
+#pragma unroll
+        for (int u = 0; u < kNormUnroll; ++u) {
+            pos[u] = e;
+            e += de;
+            if (e >= dlen) e -= dlen;
+            if (i + u * threads < n4) v[u] = d4[i + u * threads];
+        }
+#pragma unroll
+        for (int u = 0; u < kNormUnroll; ++u) {
+            if (i + u * threads < n4) {
+                int p = pos[u];
+                float4 r;
+                r.x = apply(v[u].x, p);
+                p = p + 1 == dlen ? 0 : p + 1;
+                r.y = apply(v[u].y, p);
+                p = p + 1 == dlen ? 0 : p + 1;
+                r.z = apply(v[u].z, p);
+                p = p + 1 == dlen ? 0 : p + 1;
+                r.w = apply(v[u].w, p);
+                d4[i + u * threads] = r;
+            }
+        }
     }
+    // the last total % 4 elements
+    const int64_t tail = (n4 << 2) + t0;
+    if (tail < total) desc[tail] = apply(desc[tail], static_cast<int>(tail % dlen));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -228,11 +294,38 @@ __global__ void __launch_bounds__(kPThreads) project_kernel(const float* __restr
     }
 }
 
-__global__ void absdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count, double* __restrict__ out) {
+// sum |a - b| in fp64.  128-bit loads, kDiffUnroll pairs of them in flight per thread (one element per iteration kept one
+// load in flight per warp: 2.3 TB/s); `vec` is false when a pointer is not 16-byte aligned (sub-views of a projection array).
+constexpr int kDiffUnroll = 4;
+__global__ void __launch_bounds__(256) absdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count, bool vec,
+                                                          double* __restrict__ out) {
     double acc = 0.0;
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < count;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
-        acc += static_cast<double>(fabsf(__ldg(a + idx) - __ldg(b + idx)));
+    const int64_t threads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t t0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    int64_t done = 0;
+    if (vec) {
+        const int64_t n4 = count >> 2;
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        for (int64_t i = t0; i < n4; i += kDiffUnroll * threads) {
+            float4 va[kDiffUnroll], vb[kDiffUnroll];
+#pragma unroll
+            for (int u = 0; u < kDiffUnroll; ++u) {
+                const bool ok = i + u * threads < n4;
+                va[u] = ok ? __ldg(a4 + i + u * threads) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[u] = ok ? __ldg(b4 + i + u * threads) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kDiffUnroll; ++u) {
+                acc += static_cast<double>(fabsf(va[u].x - vb[u].x));
+                acc += static_cast<double>(fabsf(va[u].y - vb[u].y));
+                acc += static_cast<double>(fabsf(va[u].z - vb[u].z));
+                acc += static_cast<double>(fabsf(va[u].w - vb[u].w));
+            }
+        }
+        done = n4 << 2;
+    }
+    for (int64_t idx = done + t0; idx < count; idx += threads) acc += static_cast<double>(fabsf(__ldg(a + idx) - __ldg(b + idx)));
     acc = warp_sum(acc);
     __shared__ double s_part[32];
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -282,9 +375,14 @@ extern "C" int bgan_swd_extract_f32(const float* level, int n, int c, int h, int
     const int64_t n_desc = static_cast<int64_t>(n) * nhoods_per_image;
     const int64_t total = n_desc * c * nhood * nhood;
     (void)total;
-    const int64_t ctas = std::min<int64_t>(ceil_div64(n_desc, 8), 8 * static_cast<int64_t>(device_sm_count()));
-    extract_kernel<4><<<static_cast<unsigned>(ctas), 256, 0, static_cast<cudaStream_t>(stream)>>>(level, c, h, w, px, py, nhoods_per_image,
-                                                                                              nhood, n_desc, desc_out, sums);
+    const int64_t ctas = std::min<int64_t>(ceil_div64(n_desc, 8), 2 * static_cast<int64_t>(device_sm_count()));
+    const int dlen = c * nhood * nhood;
+    BGAN_REQUIRE(dlen <= 32 * 16, BGAN_E_UNSUPPORTED, "bgan_swd_extract_f32: descriptors of more than 512 floats are not supported (got %d)", dlen);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dlen <= 32 * 5)  // 7 x 7 x 3 = 147: five elements per lane
+        extract_kernel<4, 5><<<static_cast<unsigned>(ctas), 256, 0, st>>>(level, c, h, w, px, py, nhoods_per_image, nhood, n_desc, desc_out, sums);
+    else
+        extract_kernel<4, 16><<<static_cast<unsigned>(ctas), 256, 0, st>>>(level, c, h, w, px, py, nhoods_per_image, nhood, n_desc, desc_out, sums);
     BGAN_LAUNCH_OK();
     return 0;
 }
@@ -351,7 +449,9 @@ extern "C" int bgan_swd_normalise_f32(float* desc, int64_t rows, int c, int per_
     BGAN_REQUIRE(desc && sums && rows > 0 && c > 0 && c <= 8 && per_channel > 0 && count > 0, BGAN_E_BADARG,
                  "bgan_swd_normalise_f32: bad arguments");
     const int64_t total = rows * c * per_channel;
-    normalise_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(desc, total, c, per_channel, sums, count);
+    BGAN_REQUIRE(reinterpret_cast<uintptr_t>(desc) % 16 == 0, BGAN_E_BADARG, "bgan_swd_normalise_f32: desc must be 16-byte aligned");
+    normalise_kernel<<<grid_for(ceil_div64(total, 4 * kNormUnroll), 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(desc, total, c, per_channel,
+                                                                                                                     sums, count);
     BGAN_LAUNCH_OK();
     return 0;
 }
@@ -390,7 +490,8 @@ extern "C" int bgan_swd_project_f32(const float* desc, int64_t rows, int k, cons
 
 extern "C" int bgan_swd_absdiff_sum_f32(const float* a, const float* b, int64_t count, double* sum_out, void* stream) {
     BGAN_REQUIRE(a && b && sum_out && count > 0, BGAN_E_BADARG, "bgan_swd_absdiff_sum_f32: bad arguments");
-    absdiff_sum_kernel<<<grid_for(count, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, count, sum_out);
+    const bool vec = reinterpret_cast<uintptr_t>(a) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0;
+    absdiff_sum_kernel<<<grid_for(ceil_div64(count, 4 * kDiffUnroll), 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, count, vec, sum_out);
     BGAN_LAUNCH_OK();
     return 0;
 }

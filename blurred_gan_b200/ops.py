@@ -383,3 +383,34 @@ def swd_absdiff_sum(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         rc = _lib.load().bgan_swd_absdiff_sum_f32(a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream_ptr())
     _lib.check(rc, "bgan_swd_absdiff_sum_f32")
     return out
+
+
+def swd_sort_diff_(a: torch.Tensor, b: torch.Tensor, sums: torch.Tensor, seg_offset: int, segs_per_sum: int,
+                   scratch: dict | None = None) -> torch.Tensor:
+    """``sums[(s + seg_offset) // segs_per_sum] += sum |sort(a[s]) - sort(b[s])|`` for every row s of a, b [segments, rows]
+    through ONE library call (``bgan_swd_sort_diff_f32``): a is sorted in place, b is clobbered, the sorted b is never
+    stored.  ``sums``: fp64 CUDA tensor.  Returns ``sums``."""
+    _require_cuda(a, "swd_sort_diff_")
+    _require_cuda(b, "swd_sort_diff_")
+    assert a.is_contiguous() and b.is_contiguous() and a.dim() == 2 and a.shape == b.shape and a.device == b.device
+    assert sums.is_cuda and sums.dtype == torch.float64 and sums.is_contiguous() and sums.device == a.device
+    segments, rows = a.shape
+    n_sums = sums.numel()
+    lib = _lib.load()
+    with _on_device(a.device):
+        done = 0
+        while done < segments:  # the kernel grid caps segments per launch
+            seg = min(segments - done, 32768)
+            ws_bytes = lib.bgan_swd_sort_diff_workspace_bytes(rows, seg, n_sums)
+            ws = scratch.get("sort_ws") if scratch is not None else None
+            if ws is None or ws.numel() < ws_bytes or ws.device != a.device:
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+                if scratch is not None:
+                    scratch["sort_ws"] = ws
+            rc = lib.bgan_swd_sort_diff_f32(a[done : done + seg].data_ptr(), b[done : done + seg].data_ptr(), rows, seg, seg_offset + done,
+                                            segs_per_sum, n_sums, sums.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr())
+            _lib.check(rc, "bgan_swd_sort_diff_f32")
+            if scratch is None:
+                ws.record_stream(torch.cuda.current_stream(a.device))
+            done += seg
+    return sums

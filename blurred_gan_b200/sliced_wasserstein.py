@@ -105,11 +105,10 @@ def sliced_wasserstein(A, B, dir_repeats, dirs_per_repeat, group=None, scratch=N
     if block.stop > block.start:
         dirs_t = torch.from_numpy(np.ascontiguousarray(dirs[:, block])).to(A.device)
         nd = block.stop - block.start
-        # [directions of this rank, rows], each row sorted
-        projA = ops.swd_sort_(ops.swd_project(A, dirs_t, out=_scratch_proj(scratch, "projA", nd, rows, A.device)), scratch)
-        projB = ops.swd_sort_(ops.swd_project(B, dirs_t, out=_scratch_proj(scratch, "projB", nd, rows, A.device)), scratch)
-        for rep, lo, hi in _dist.repeat_segments(block, dirs_per_repeat):
-            partial[rep : rep + 1] += ops.swd_absdiff_sum(projA[lo:hi], projB[lo:hi])
+        # [directions of this rank, rows]; sort both, sum |A - B| per repeat: one library call (the sorted B is never stored)
+        projA = ops.swd_project(A, dirs_t, out=_scratch_proj(scratch, "projA", nd, rows, A.device))
+        projB = ops.swd_project(B, dirs_t, out=_scratch_proj(scratch, "projB", nd, rows, A.device))
+        ops.swd_sort_diff_(projA, projB, partial, block.start, dirs_per_repeat, scratch)
     return np.float32(_dist.combine_repeat_sums(partial, rows, dirs_per_repeat, group))
 
 

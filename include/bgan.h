@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BGAN_ABI_VERSION 2 /* 2: + bgan_blur2d_multi_f32, bgan_lerp_rows_f32, bgan_swd_feed_f32 (+ workspace query) */
+#define BGAN_ABI_VERSION 3 /* 2: + bgan_blur2d_multi_f32, bgan_lerp_rows_f32, bgan_swd_feed_f32; 3: + bgan_swd_sort_diff_f32 */
 
 /* tap rules */
 #define BGAN_RULE_TORCH 0    /* pytorch/gaussianblur.py:9-14 (normaliser inside the exp)  */
@@ -92,8 +92,9 @@ int bgan_lerp_rows_f32(const float* u_device, const float* v_device, const float
 
 /* How the last bgan_blur2d_f32 / bgan_blur2d_multi_f32 call on this thread was executed: 1 = fused tile kernel with TMA
  * staging, 2 = fused tile kernel with plain loads, 3 = two launches (row pass, column pass), 4 = tcgen05 tensor-core kernel (128 x 128 planes),
- * 5 = direct FFMA kernel for 128 x 128 images with radius <= 5 (NHWC: 4), 6 = two-pass tcgen05 kernel for planes of
- * 256 x 256 and more with radius 12 .. 256 (needs the workspace). */
+ * 5 = direct FFMA kernel for 128 x 128 images with radius <= 4 (radius 5 only with caller-supplied taps), 6 = two-pass tcgen05 kernel for planes of
+ * 256 x 256 and more with radius 12 .. 256 (needs the workspace), 7 = the same for NHWC images with 2 .. 4 channels:
+ * interleaved -> planar copy, path 6 on the channel planes, planar -> interleaved (needs the workspace). */
 int bgan_blur2d_last_path(void);
 
 /* ------------------------------------------------------------------------------------ */
@@ -152,6 +153,17 @@ int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws_d
 /* sliced_wasserstein.py:49-50  *sum_out_device += sum_i |a[i] - b[i]| (fp64; caller zeroes it). */
 int bgan_swd_absdiff_sum_f32(const float* a_device, const float* b_device, int64_t count, double* sum_out_device,
                              void* stream);
+
+/* sliced_wasserstein.py:47-50 as ONE call: sort every segment of a_device in place (ascending), sort the segments of
+ * b_device, and add sum_i |sort(a)[i] - sort(b)[i]| of segment s to sums_device[(s + seg_offset) / segs_per_sum] (fp64,
+ * accumulated into; n_sums entries).  The last radix pass over b does not write the keys: every key meets the element of the
+ * sorted a that sits at its final position and only the distance is accumulated -- the sorted b is never stored and the
+ * separate |a - b| pass disappears.  b_device is clobbered (partially sorted on return).  a and b: `segments` contiguous
+ * runs of `rows` floats.  seg_offset / segs_per_sum: a rank that owns directions [seg_offset, seg_offset + segments) of the
+ * dir_repeats x dirs_per_repeat matrix passes segs_per_sum = dirs_per_repeat and gets one sum per repeat. */
+size_t bgan_swd_sort_diff_workspace_bytes(int64_t rows, int segments, int n_sums);
+int bgan_swd_sort_diff_f32(float* a_device, float* b_device, int64_t rows, int segments, int seg_offset, int segs_per_sum,
+                           int n_sums, double* sums_device, void* ws_device, size_t ws_bytes, void* stream);
 
 /* Host-only.  Bit-exact replay of numpy's legacy np.random.randint(low, high, size=count) -- the call behind the patch
  * positions of sliced_wasserstein.py:20-21 -- on a caller-held MT19937 state: key624 / *pos_inout are the `key` and `pos`

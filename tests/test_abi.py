@@ -74,7 +74,9 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     # large planes, wide blur: transposed intermediate + row maxima of the two-pass tensor-core path
     plane = 2 * 3 * 1024 * 1024 * 4
     assert plane <= lib.bgan_blur2d_workspace_bytes(2, 3, 1024, 1024, 0, 160) <= plane + 2 * 3 * 2048 * 4 + 512
-    assert lib.bgan_blur2d_workspace_bytes(2, 3, 1024, 1024, 1, 160) == plane                     # NHWC: two launches of the tile kernel
+    # NHWC, 3 channels: planar copy + the two-pass tensor-core kernel's scratch on the channel planes (path 7)
+    assert 2 * plane <= lib.bgan_blur2d_workspace_bytes(2, 3, 1024, 1024, 1, 160) <= 2 * plane + 2 * 3 * 2048 * 4 + 1024
+    assert lib.bgan_blur2d_workspace_bytes(2, 3, 1024, 1024, 1, 300) == plane                     # radius > 256: two launches of the tile kernel
 
 
 def test_new_entry_points_validate_their_arguments_without_a_gpu(lib):
@@ -109,3 +111,17 @@ def test_new_entry_points_validate_their_arguments_without_a_gpu(lib):
     assert lib.bgan_swd_feed_f32(256, n, c, 128, 128, 4, 512, 128, 7, four, four, None, 0, None) < 0            # workspace missing
     assert b"workspace" in lib.bgan_last_error()
     assert lib.bgan_swd_feed_f32(256, n, c, 100, 100, 4, 512, 128, 7, four, four, 2048, 1 << 30, None) < 0      # 100 does not halve 3 times
+
+
+_lib_E_WORKSPACE = -2  # BGAN_E_WORKSPACE
+
+
+def test_sort_diff_validates_its_arguments_without_a_gpu(lib):
+    """bgan_swd_sort_diff_f32 (sort + |A - B| fused): argument and workspace errors before any CUDA call."""
+    assert lib.bgan_swd_sort_diff_f32(None, None, 10, 1, 0, 1, 1, None, None, 0, None) < 0
+    assert lib.bgan_swd_sort_diff_f32(256, 512, 10, 4, 0, 2, 1, 768, 1024, 1 << 30, None) < 0   # segments 0..3 / 2 -> sums 0..1, only 1 given
+    assert b"do not map" in lib.bgan_last_error()
+    assert lib.bgan_swd_sort_diff_f32(256, 512, 10, 4, 126, 128, 1, 768, 1024, 1 << 30, None) < 0  # offset pushes the last segment into sum 1
+    assert lib.bgan_swd_sort_diff_f32(256, 512, 10, 4, 0, 2, 2, 768, 1024, 16, None) == _lib_E_WORKSPACE
+    assert lib.bgan_swd_sort_diff_workspace_bytes(1 << 18, 64, 4) >= lib.bgan_swd_sort_workspace_bytes(1 << 18, 64) + 4 * 64 * 8
+    assert lib.bgan_swd_sort_diff_workspace_bytes(0, 64, 4) == 0

@@ -120,7 +120,8 @@ def test_ragged_shapes_both_rules(shape, layout):
 @pytest.mark.parametrize("std", [8.0, 32.0, 64.0])
 def test_large_image_wide_halo(std, monkeypatch):
     """BASELINE configs[3] shape (1024 x 1024, std up to 64), reduced batch for the CPU oracle.  NCHW planes run on the
-    two-pass tensor-core kernel (path 6); with it disabled, and for NHWC, on the CUDA-core tile kernel."""
+    two-pass tensor-core kernel (path 6), NHWC images on the same kernel between two layout conversions (path 7); with it
+    disabled, on the CUDA-core tile kernel."""
     from blurred_gan_b200 import ops
     from blurred_gan_b200.gaussian_blur import blur_images
     from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
@@ -137,8 +138,17 @@ def test_large_image_wide_halo(std, monkeypatch):
     if std >= 64.0:
         assert ops.last_blur_path() == 3  # row pass + column pass through scratch
     monkeypatch.delenv("BGAN_BLUR_NO_AXIS_TC")
+    # NHWC (the reference's own layout, gaussian_blur.py:111-130): interleaved -> planar, the same two passes, planar -> interleaved
     xh = uniform_pm1(7, (1, 1024, 1024, 3))
-    assert_close(blur_images(_dev(xh), std), bo.blur_images_tf_ref(xh, std), "tf NHWC 1024 std=%g" % std)
+    xh[0, :, :, 2] *= 3e-4
+    want_h = bo.blur_images_tf_ref(xh, std)
+    got_h = blur_images(_dev(xh), std)
+    assert ops.last_blur_path() == 7
+    for c in range(3):
+        assert_close(got_h[0, :, :, c], want_h[0, :, :, c], "tf NHWC 1024 channel %d std=%g" % (c, std))
+    monkeypatch.setenv("BGAN_BLUR_NO_AXIS_TC", "1")
+    assert_close(blur_images(_dev(xh[:, :256]), std), bo.blur_images_tf_ref(xh[:, :256], std), "tf NHWC 256 x 1024 std=%g (tile kernel)" % std)
+    assert ops.last_blur_path() in (1, 2, 3)
 
 
 @pytest.mark.parametrize("shape,std", [((2, 1, 256, 256), 6.0), ((1, 3, 300, 260), 9.0), ((1, 2, 512, 384), 40.0), ((3, 1, 260, 516), 20.0)])
@@ -340,7 +350,8 @@ def test_tensor_core_pipeline_plane_counts(planes):
 
 @pytest.mark.parametrize("std", [0.5, 3.0, 23.0])
 def test_tensor_core_path_nhwc(std, monkeypatch):
-    """NHWC 128 x 128 x 3 (the layout of the reference's Keras layer): TMA deinterleaves with element stride 3."""
+    """NHWC 128 x 128 x 3 (the layout of the reference's Keras layer): the compute warps gather one channel plane with 4-byte
+    cp.async (TMA cannot walk the innermost dimension with an element stride), the stores scatter with stride 3."""
     from blurred_gan_b200 import ops
     from blurred_gan_b200.gaussian_blur import GaussianBlur2D
 

@@ -210,6 +210,35 @@ def test_api_matches_oracle_larger():
     np.testing.assert_allclose(got[1], want[1], rtol=1e-4)
 
 
+@pytest.mark.parametrize("rows,segments,seg_offset,per_sum,n_sums", [(5000, 6, 0, 3, 2), (4096, 4, 126, 128, 2), (70001, 3, 5, 2, 4), (1, 2, 0, 1, 2),
+                                                                   (262144, 8, 0, 4, 2)])
+def test_fused_sort_diff_is_the_sort_then_the_distance(rows, segments, seg_offset, per_sum, n_sums):
+    """bgan_swd_sort_diff_f32 (sliced_wasserstein.py:47-50 in one call): a comes back sorted bit for bit like np.sort, the
+    sums are sum |sort(a) - sort(b)| per group of segments (fp64 of the fp32 differences; accumulated INTO sums)."""
+    from blurred_gan_b200 import ops
+
+    rs = np.random.RandomState(rows % 1000 + segments)
+    a = (rs.randn(segments, rows) * np.exp(rs.randn(segments, 1))).astype(np.float32)
+    b = (rs.randn(segments, rows) * 1.3 + 0.2).astype(np.float32)
+    a[0, : min(rows, 7)] = [0.0, -0.0, np.float32(1e-40), -np.float32(1e-40), 3e38, -3e38, 1.0][: min(rows, 7)]  # signed zeros, subnormals, extremes
+    sums = torch.full((n_sums,), 0.5, dtype=torch.float64, device="cuda")
+    ad, bd = _dev(a), _dev(b)
+    ops.swd_sort_diff_(ad, bd, sums, seg_offset, per_sum)
+    sa, sb = np.sort(a, axis=1), np.sort(b, axis=1)
+    got_a = ad.cpu().numpy()
+    np.testing.assert_array_equal(got_a, sa)
+    want = np.full(n_sums, 0.5)
+    for s in range(segments):
+        want[(s + seg_offset) // per_sum] += np.abs(sa[s] - sb[s]).astype(np.float64).sum()
+    np.testing.assert_allclose(sums.cpu().numpy(), want, rtol=1e-12)
+    # the same through the two separate calls
+    ad2, bd2 = ops.swd_sort_(_dev(a)), ops.swd_sort_(_dev(b))
+    assert torch.equal(ad2, ad)
+    for s in range(segments):
+        sep = float(ops.swd_absdiff_sum(ad2[s], bd2[s]).item())
+        assert sep == pytest.approx(np.abs(sa[s] - sb[s]).astype(np.float64).sum(), rel=1e-12)
+
+
 def test_api_matches_reference_golden_at_baseline_scale():
     """2 x 2048 images (262,144 descriptors per level and set: 64 sort tiles per direction, 2048 row tiles of the tensor-core
     projection) against the UNMODIFIED reference, run once in the build container (tests/golden/make_golden.py --swd-large;

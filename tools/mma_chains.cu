@@ -138,119 +138,15 @@ void run(int n, int mode, int sms, long long* d_cycles, long long* h) {
 }
 
 
-// W issuing warps (one thread each), every warp accumulates into its own TMEM columns and commits to its own barriers:
-// is the per-instruction floor a property of the tensor pipe or of one thread's issue path?
-template <int W>
-__global__ void __launch_bounds__(128, 1) mma_warps_kernel(int n, int mode, long long* cycles_out) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // (static shared memory precedes the dynamic part: align by hand, SWIZZLE_128B descriptors need a 1024-byte base)
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t bar[2 * W];
-    __shared__ uint32_t s_tmem;
-    __shared__ long long s_cyc[W];
-    for (uint32_t i = threadIdx.x; i < kSmem / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * W; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[i])), "r"(1) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
-    {
-        const uint32_t taddr = tmem + (static_cast<uint32_t>((threadIdx.x >> 5) * 32) << 16);
-        for (int c = 0; c < 64; c += 16) {
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr + c),
-                "r"(0)
-                : "memory");
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int warp = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0 && warp < W) {
-        const uint32_t id = idesc(n);
-        const uint32_t d = tmem + 64 + static_cast<uint32_t>(warp * n);
-        uint64_t* mybar = bar + 2 * warp;
-        const uint64_t adesc = desc_sw128(smem_u32(smem)), bdesc = desc_sw128(smem_u32(smem) + 16384);
-        long long t0 = 0;
-        int batch = 0;
-        for (int rep = 0; rep < 2; ++rep) {
-            t0 = clock64();
-            for (int b = 0; b < kBatches; ++b, ++batch) {
-#pragma unroll
-                for (int k = 0; k < kPerBatch; ++k) {
-                    const uint64_t ks = static_cast<uint64_t>((k & 3) * 2);
-                    if (mode == 0)
-                        mma_ss(d, adesc + ks, bdesc + ks, id, k > 0);
-                    else
-                        mma_ts(d, tmem + 8 * (k & 7), bdesc + ks, id, k > 0);
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mybar[batch & 1]))
-                             : "memory");
-                if (b > 0) wait_bar(&mybar[(batch - 1) & 1], ((batch - 1) >> 1) & 1);
-            }
-            wait_bar(&mybar[(batch - 1) & 1], ((batch - 1) >> 1) & 1);
-        }
-        s_cyc[warp] = clock64() - t0;
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long m = 0;
-        for (int i = 0; i < W; ++i) m = s_cyc[i] > m ? s_cyc[i] : m;
-        cycles_out[blockIdx.x] = m;
-    }
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
-}
-
-template <int W>
-void run_warps(int n, int mode, int sms, long long* d_cycles, long long* h) {
-    if (64 + W * n > 512) return;
-    cudaFuncSetAttribute(mma_warps_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem + 1024));
-    mma_warps_kernel<W><<<sms, 128, kSmem + 1024>>>(n, mode, d_cycles);
-    const cudaError_t err = cudaDeviceSynchronize();
-    if (err != cudaSuccess) {
-        printf("warps %d mode %d N %d: %s\n", W, mode, n, cudaGetErrorString(err));
-        exit(1);
-    }
-    cudaMemcpy(h, d_cycles, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
-    long long mx = 0;
-    for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
-    const double per = static_cast<double>(mx) / (kBatches * kPerBatch * W);
-    printf("A from %s  N=%3d  issuing warps=%d : %7.1f cycles per MMA (all warps together)   %6.1f per 128x128x16 equivalent\n",
-           mode == 0 ? "smem" : "TMEM", n, W, per, per * 128.0 / n);
-}
-
 }  // namespace
 
-int main(int argc, char** argv) {
+int main() {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     long long* d_cycles = nullptr;
     cudaMalloc(&d_cycles, sizeof(long long) * sms);
     long long* h = static_cast<long long*>(malloc(sizeof(long long) * sms));
     printf("tcgen05.mma kind::f16 M=128 K=16, %d SMs, %d MMAs per SM rotating over `chains` independent accumulators\n", sms, kBatches * kPerBatch);
-    if (argc > 1 && atoi(argv[1]) == 2) {
-        printf("several issuing warps, one accumulator chain each\n");
-        for (int mode = 0; mode < 2; ++mode)
-            for (int n : {64, 128, 192, 224}) {
-                run_warps<1>(n, mode, sms, d_cycles, h);
-                run_warps<2>(n, mode, sms, d_cycles, h);
-                run_warps<3>(n, mode, sms, d_cycles, h);
-                run_warps<4>(n, mode, sms, d_cycles, h);
-            }
-        return 0;
-    }
     for (int mode = 0; mode < 2; ++mode)
         for (int n : {32, 64, 128, 224}) {
             run<1>(n, mode, sms, d_cycles, h);
