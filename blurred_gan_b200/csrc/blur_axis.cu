@@ -60,7 +60,17 @@ struct AxisArgs {
     float std_eff;
     int radius;
     const float* taps_dev;
+    long long* trace;         // debug: clock64 stamps of CTA 0 of the sweep kernel (nullptr in production), tools/trace_axis.py
 };
+
+// trace layout: three timelines of 256 int64 each (compute thread 0, MMA lane, lane 0 of the first store warp);
+// entry 0 of a timeline = number of stamps that follow
+__device__ __forceinline__ void ax_stamp(long long* trace, int role, int& n) {
+    if (trace != nullptr && blockIdx.x == 0 && n < 254) {
+        trace[role * 256 + 1 + n] = clock64();
+        trace[role * 256] = ++n;
+    }
+}
 
 __device__ __forceinline__ uint32_t ax_tile_off(int row, int k) {
     return (k >> 6) * kAKBlock + row * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
@@ -339,6 +349,8 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
             // row scales of this tile.  s_scale is only read by the compute warps (the barrier at the end of the previous
             // block ordered those reads); s_inv[n & 1] was last read by the store warps for tile n - 2.
             if (n >= 2) mbar_wait(mbar_acc_free + (n & 1), ((n - 2) >> 1) & 1);
+            named_bar_sync(3, kAxThreads);  // (the hand-over to the MMA warp no longer blocks: a fast warp must not replace
+                                            //  the scales while a slow one still converts the previous tile's last block)
             if (tid < kB) {
                 const int i = c.ib * kB + tid;
                 const float m = i < a.I ? __ldg(a.rowmax_in + static_cast<size_t>(c.plane) * a.I + i) : 0.0f;
@@ -369,6 +381,21 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
                         v[q] = *reinterpret_cast<const float4*>(stage + h * kB + w);
                     }
                 }
+                // The row scale is applied BEFORE the barrier that releases the staging buffer to the next TMA load: the
+                // multiplications consume the loaded registers, so every LDS has really returned when the thread arrives.  (A
+                // load that is only issued can still sit in the LSU queue -- behind the store warps' scattered stores for
+                // thousands of cycles -- when the barrier completes, and would then read the next block: seen once in
+                // ~10 runs as a 6 % error in one plane of test_axis_tensor_core_path_many_work_units_per_cta.)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q < nks) {
+                        int h, w;
+                        locate(q, h, w);
+                        const float sc = s_scale[h];
+                        v[q].x *= sc, v[q].y *= sc, v[q].z *= sc, v[q].w *= sc;
+                        asm volatile("" ::"f"(v[q].x), "f"(v[q].y), "f"(v[q].z), "f"(v[q].w));  // (pins the products in front of the barrier)
+                    }
+                }
                 named_bar_sync(3, kAxThreads);  // staging drained
                 if (tid == 0) {
                     issue_load();       // block u + 1 (in L2 already)
@@ -383,10 +410,9 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
                     if (q < nks) {
                         int h, w;
                         locate(q, h, w);
-                        const float sc = s_scale[h];
                         __half2 hi[2], lo[2];
-                        ax_split2(v[q].x * sc, v[q].y * sc, hi[0], lo[0]);
-                        ax_split2(v[q].z * sc, v[q].w * sc, hi[1], lo[1]);
+                        ax_split2(v[q].x, v[q].y, hi[0], lo[0]);
+                        ax_split2(v[q].z, v[q].w, hi[1], lo[1]);
                         const uint32_t off = ax_tile_off(h, w);
                         *reinterpret_cast<uint2*>(x1 + off) = *reinterpret_cast<uint2*>(hi);
                         *reinterpret_cast<uint2*>(x2 + off) = *reinterpret_cast<uint2*>(lo);
@@ -401,6 +427,328 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_tc_kernel(const AxisArgs 
     ax_fence_before();
     __syncthreads();
     if (warp == kAxWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+
+// =====================================================================================================================
+// Radius <= 128 (nb = 1): input-stationary sweep.  A CTA takes a strip -- 128 input rows i of one plane -- and walks the
+// blocks L = 0, 1, ... along the blurred axis.  Every block is loaded and converted ONCE and multiplied into the (up to)
+// three output tiles it touches, J = L - 1 (which it completes), L and L + 1 (which it starts); the tile kernel above loads
+// and converts every block three times, once per tile, and with one 64 KB TMA box in flight per SM that latency, not the
+// tensor pipe, was its limit (profiles/r02_axis.md).  Three live accumulators + one being drained = 4 x 128 TMEM columns,
+// which needs ONE accumulator per tile: the taps are stored scaled by 2^11 (T' = 2^11 T, hi = fp16(T'), lo = fp16(T' - hi):
+// the remainder of even a tiny tap stays above fp16's subnormal range relative to what matters), the data remainders
+// unscaled (rows are scaled to [2^12, 2^13)), so T' X ~= T'_hi X_hi + T'_hi X_lo + T'_lo X_hi accumulates in any order and
+// the epilogue multiplies by 2^-11 / scale_i.
+constexpr int kSwSlots = 4;
+// Threads: 8 conversion warps, the MMA-issuing warp, 8 store warps (two per TMEM lane quadrant).
+// The output leaves through shared memory and TMA stores.  clock64 timelines of the first versions (profiles/r02_axis.md):
+// an accumulator row is an output row, so a direct store has its 32 lanes in 32 different lines -- 4096 sixteen-byte store
+// requests per tile -- and those requests, not the tensor pipe, set the pace: they also starved the conversion warps' own
+// LDS / STS, which share the LSU.  Now a store warp writes its 32 rows x 32 columns into a 128-byte-swizzled box (conflict
+// free) and one thread hands two such boxes at a time to the TMA, which writes whole 128-byte row segments off the LSU.
+constexpr int kSwCompute = 256;
+constexpr int kSwComputeWarps = kSwCompute / 32;
+constexpr int kSwStoreWarps = 8;
+constexpr int kSwStoreThreads = 32 * kSwStoreWarps;
+constexpr int kSwCta = kSwCompute + 32 + kSwStoreThreads;  // 544
+// shared memory: input staging, a ring of 3 quarter blocks (32 rows, 16 KB each) | X[2][hi | lo] 128 KB | output boxes
+// 2 x 16 KB | strips 2 x 8 KB (63 core matrices each) | scales, barriers.  (With one half block in flight the ~1500 cycles
+// of an L2-hit TMA load were exposed twice per block; three quarter blocks in flight hide them.)
+constexpr int kSwRing = 3;
+constexpr int kSwChunkRows = 32;
+constexpr uint32_t kSwChunk = kSwChunkRows * kB * 4;  // 16384
+constexpr uint32_t kSwStage = kSwRing * kSwChunk;      // 49152
+constexpr uint32_t kSwOffX = kSwStage;
+constexpr uint32_t kSwOffOut = kSwOffX + 4 * kATile;
+constexpr uint32_t kSwOutBox = kB * 128;           // 128 output rows x 32 columns of fp32
+constexpr uint32_t kSwStrip = 8192;
+constexpr uint32_t kSwOffS1 = kSwOffOut + 2 * kSwOutBox;
+constexpr uint32_t kSwOffS2 = kSwOffS1 + kSwStrip;
+constexpr uint32_t kSwOffMisc = kSwOffS2 + kSwStrip;
+constexpr uint32_t kSwSmem = kSwOffMisc + 1536 + 256;
+static_assert(kSwSmem <= 227 * 1024, "sweep kernel: shared memory");
+
+__device__ __forceinline__ void sw_split_tap2(float a, float b, __half2& hi, __half2& lo) {
+    a *= 2048.0f;
+    b *= 2048.0f;
+    hi = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hi);
+    lo = __floats2half2_rn(a - back.x, b - back.y);
+}
+__device__ __forceinline__ void sw_split_raw2(float a, float b, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hi);
+    lo = __floats2half2_rn(a - back.x, b - back.y);
+}
+// 3-D tiled TMA store: dense (swizzled) smem box -> box at (c0, c1, c2) of the tensor; out-of-bounds parts are not written
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct SweepMaps {
+    CUtensorMap in;   // [planes][I][K] fp32, box {128 k, 32 i, 1}
+    CUtensorMap out;  // [planes][K][I] fp32, box {32 i, 128 j, 1}, SWIZZLE_128B
+};
+
+__global__ void __launch_bounds__(kSwCta, 1) blur_axis_sweep_kernel(const AxisArgs a, const __grid_constant__ SweepMaps maps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* s_g = reinterpret_cast<float*>(smem + kSwOffX);  // taps, only until the strip of core matrices is built
+    float* s_scale = reinterpret_cast<float*>(smem + kSwOffMisc);  // [128] per input row of the strip being converted
+    float* s_inv = s_scale + kB;                                   // [2][128]: strip parity (read by the store warps)
+    uint64_t* mbar_tma = reinterpret_cast<uint64_t*>(smem + kSwOffMisc + 1536);  // [3]: ring slot filled
+    uint64_t* mbar_mma = mbar_tma + kSwRing;           // [2]: the MMAs reading X[set] are complete
+    uint64_t* mbar_acc_full = mbar_mma + 2;            // [4]: accumulator slot holds a finished tile
+    uint64_t* mbar_acc_free = mbar_acc_full + kSwSlots;  // [4]: the store warps have read the slot
+    uint64_t* mbar_strip_done = mbar_acc_free + kSwSlots;  // [2]: the store warps are done with a strip (its s_inv)
+    double* s_red = reinterpret_cast<double*>(mbar_strip_done + 2);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_strip_done + 3);
+    const uint32_t sbase = smem_u32(smem);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int TJ = a.tiles_j;
+    const int n_strips = a.planes * a.tiles_i;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        tma_prefetch_desc(&maps.in);
+        tma_prefetch_desc(&maps.out);
+        for (int b = 0; b < kSwRing; ++b) mbar_init(mbar_tma + b, 1);
+        mbar_init(mbar_mma + 0, 1);
+        mbar_init(mbar_mma + 1, 1);
+        for (int b = 0; b < kSwSlots; ++b) {
+            mbar_init(mbar_acc_full + b, 1);
+            mbar_init(mbar_acc_free + b, kSwStoreWarps);
+        }
+        mbar_init(mbar_strip_done + 0, kSwStoreWarps);
+        mbar_init(mbar_strip_done + 1, kSwStoreWarps);
+        mbar_fence_init();
+    }
+    if (warp == kSwComputeWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (a.rule == BGAN_RULE_EXPLICIT) asm volatile("griddepcontrol.wait;" ::: "memory");
+    normalised_taps(a.rule, a.std_eff, a.radius, a.taps_dev, s_g, s_red);  // (ends with __syncthreads)
+    {   // the strip of core matrices (as in the tile kernel, nb = 1), taps scaled by 2^11
+        const int n_taps = 2 * a.radius + 1, mats = 32 + 31;
+        for (int j = tid; j < mats * 32; j += kSwCta) {
+            const int m = j >> 5, rho = (j >> 2) & 7, e = j & 3;
+            const int ta = 8 * (m - 16 - 15) - rho + a.radius + 2 * e, tb = ta + 1;
+            __half2 hi, lo;
+            sw_split_tap2((ta >= 0 && ta < n_taps) ? s_g[ta] : 0.0f, (tb >= 0 && tb < n_taps) ? s_g[tb] : 0.0f, hi, lo);
+            *reinterpret_cast<__half2*>(smem + kSwOffS1 + m * 128 + rho * 16 + e * 4) = hi;
+            *reinterpret_cast<__half2*>(smem + kSwOffS2 + m * 128 + rho * 16 + e * 4) = lo;
+        }
+    }
+    fence_proxy_async();
+    ax_fence_before();
+    __syncthreads();
+    ax_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int jl = ((warp & 3) * 32 + lane) ^ kARev;  // output row (inside the tile) held by this lane's accumulator row
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if (warp == kSwComputeWarps) {
+        // ================= MMA issuer =================================================================
+        int u = 0, base = 0;  // block counter; running index of the strip's tile 0
+        int ns = 0;
+        for (int strip = first; strip < n_strips; strip += stride, base += TJ) {
+            for (int L = 0; L < TJ; ++L, ++u) {
+                named_bar_sync(1 + (u & 1), kSwCompute + 32);  // X[u & 1] of block u written
+                if (lane == 0) {
+                    ax_stamp(a.trace, 1, ns);  // block u: operands ready
+                    ax_fence_after();
+                    const uint32_t xb = sbase + kSwOffX + (u & 1) * 2 * kATile;
+                    const uint64_t b1 = ax_desc_sw128(xb), b2 = ax_desc_sw128(xb + kATile);
+#pragma unroll 1
+                    for (int d = 1; d >= -1; --d) {  // tile J = L - d: d = +1 finishes J = L - 1, d = -1 starts J = L + 1
+                        const int J = L - d;
+                        if (J < 0 || J >= TJ) continue;
+                        const int tj = base + J, slot = tj & (kSwSlots - 1);
+                        const bool starts = L == (J > 0 ? J - 1 : 0);
+                        if (starts && tj >= kSwSlots) mbar_wait(mbar_acc_free + slot, ((tj >> 2) - 1) & 1);  // slot drained
+                        if (starts) ax_fence_after();
+                        int k0, k1;
+                        ks_range(d + 1, 1, a.radius, k0, k1);
+                        const uint64_t a1 = ax_desc(sbase + kSwOffS1 + (d + 1) * 16 * 128, 128, 128);
+                        const uint64_t a2 = ax_desc(sbase + kSwOffS2 + (d + 1) * 16 * 128, 128, 128);
+                        const uint32_t acc = tmem + slot * kB;
+                        for (int k = k0; k <= k1; ++k) {
+                            ax_mma(acc, a1 + k * 16, b1 + ax_kstep(k), !(starts && k == k0));
+                            ax_mma(acc, a1 + k * 16, b2 + ax_kstep(k), 1);
+                            ax_mma(acc, a2 + k * 16, b1 + ax_kstep(k), 1);
+                        }
+                    }
+                    ax_commit(mbar_mma + (u & 1));
+                    if (L >= 1) ax_commit(mbar_acc_full + ((base + L - 1) & (kSwSlots - 1)));  // tile L - 1 complete
+                    if (L == TJ - 1) ax_commit(mbar_acc_full + ((base + L) & (kSwSlots - 1)));  // ... and the last one
+                    ax_stamp(a.trace, 1, ns);  // block u: issued
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp > kSwComputeWarps) {
+        // ================= store warps: out[j][i] = D 2^-11 / scale_i, through swizzled boxes and TMA stores ===========
+        int base = 0, sl = 0;  // running tile index of the strip's tile 0; strips done by this CTA
+        int ns = 0;
+        const int sw_id = warp - kSwComputeWarps - 1;          // 0 .. 7
+        const int box = sw_id >> 2;                            // which of the two output boxes this warp fills
+        const bool issuer = sw_id == 0 && lane == 0;
+        const bool tracer = issuer;
+        unsigned char* obox = smem + kSwOffOut + box * kSwOutBox;
+        const uint32_t orow = static_cast<uint32_t>(jl) * 128;  // this lane's row of the box (rows are output rows)
+        for (int strip = first; strip < n_strips; strip += stride, base += TJ, ++sl) {
+            const int plane = strip / a.tiles_i, ib = strip - plane * a.tiles_i;
+            const float* inv = s_inv + (sl & 1) * kB;
+            for (int J = 0; J < TJ; ++J) {
+                const int tj = base + J, slot = tj & (kSwSlots - 1);
+                mbar_wait(mbar_acc_full + slot, (tj >> 2) & 1);
+                ax_fence_after();
+                if (tracer) ax_stamp(a.trace, 2, ns);  // tile complete in TMEM
+                const uint32_t acc = tmem + slot * kB;
+                const int j = J * kB + jl;
+                float mx = 0.0f;
+#pragma unroll 1
+                for (int round = 0; round < 2; ++round) {  // column groups {0, 1}, then {2, 3}: one per box
+                    const int cg = 2 * round + box;
+                    float dm[32];
+                    ax_ld32(acc + lane_base + cg * 32, dm);
+                    ax_ld_wait(dm);
+                    if (round == 1) {  // this warp's part of the slot has been read
+                        ax_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(mbar_acc_free + slot);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        dm[e] = dm[e] * (1.0f / 2048.0f) * inv[cg * 32 + e];
+                        mx = fmaxf(mx, fabsf(dm[e]));
+                    }
+                    if (issuer) tma_store_wait_read();               // the boxes' previous contents have left
+                    named_bar_sync(4, kSwStoreThreads);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(obox + orow + ((c ^ (jl & 7)) << 4)) = make_float4(dm[4 * c], dm[4 * c + 1], dm[4 * c + 2], dm[4 * c + 3]);
+                    fence_proxy_async();
+                    named_bar_sync(4, kSwStoreThreads);
+                    if (issuer) {
+                        tma_store_3d(&maps.out, smem + kSwOffOut, ib * kB + 2 * round * 32, J * kB, plane);
+                        tma_store_3d(&maps.out, smem + kSwOffOut + kSwOutBox, ib * kB + (2 * round + 1) * 32, J * kB, plane);
+                        tma_store_commit();
+                    }
+                }
+                if (j < a.K && a.rowmax_out != nullptr)
+                    atomicMax(reinterpret_cast<int*>(a.rowmax_out + static_cast<size_t>(plane) * a.K + j), __float_as_int(mx));
+                if (tracer) ax_stamp(a.trace, 2, ns);  // tile handed to the TMA
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mbar_strip_done + (sl & 1));  // s_inv[sl & 1] may be replaced (two strips on)
+        }
+        if (issuer) tma_store_wait_all();
+    } else {
+        // ================= conversion warps ===========================================================
+        // thread 0 walks the quarter blocks (chunks of 32 rows): (strip, L, quarter) to load into the ring / to pull into L2
+        int ld_strip = first, ld_q = 0, ld_c = 0, pf_strip = first, pf_q = 0;  // *_q = 4 L + quarter; ld_c = chunks issued
+        auto issue_load = [&]() {
+            if (ld_strip >= n_strips) return;
+            const int plane = ld_strip / a.tiles_i, ib = ld_strip - plane * a.tiles_i;
+            const int slot = ld_c % kSwRing;
+            mbar_arrive_expect_tx(mbar_tma + slot, kSwChunk);
+            tma_load_3d(smem + slot * kSwChunk, &maps.in, mbar_tma + slot, (ld_q >> 2) * kB, ib * kB + (ld_q & 3) * kSwChunkRows, plane);
+            ++ld_c;
+            if (++ld_q == 4 * TJ) {
+                ld_q = 0;
+                ld_strip += stride;
+            }
+        };
+        auto issue_prefetch = [&]() {
+            if (pf_strip >= n_strips) return;
+            const int plane = pf_strip / a.tiles_i, ib = pf_strip - plane * a.tiles_i;
+            tma_prefetch_l2_3d(&maps.in, (pf_q >> 2) * kB, ib * kB + (pf_q & 3) * kSwChunkRows, plane);
+            if (++pf_q == 4 * TJ) {
+                pf_q = 0;
+                pf_strip += stride;
+            }
+        };
+        if (tid == 0) {
+            for (int i = 0; i < kSwRing; ++i) issue_load();   // the ring
+            for (int i = 0; i < 12; ++i) issue_prefetch();    // three blocks ahead
+        }
+        int u = 0, sl = 0, ch = 0;  // blocks, strips, chunks consumed
+        int ns = 0;
+        for (int strip = first; strip < n_strips; strip += stride, ++sl) {
+            const int plane = strip / a.tiles_i, ib = strip - plane * a.tiles_i;
+            named_bar_sync(3, kSwCompute);  // every warp has converted the previous strip's last block: s_scale may change
+            if (sl >= 2) mbar_wait(mbar_strip_done + (sl & 1), ((sl - 2) >> 1) & 1);  // s_inv[sl & 1] no longer read
+            if (tid < kB) {
+                const int i = ib * kB + tid;
+                const float m = i < a.I ? __ldg(a.rowmax_in + static_cast<size_t>(plane) * a.I + i) : 0.0f;
+                int eb = (__float_as_int(m) >> 23) & 0xff;
+                eb = min(max(eb, 13), 254);
+                s_scale[tid] = __int_as_float((266 - eb) << 23);  // max |row| -> [2^12, 2^13)
+                s_inv[(sl & 1) * kB + tid] = __int_as_float((eb - 12) << 23);
+            }
+            named_bar_sync(3, kSwCompute);
+            for (int L = 0; L < TJ; ++L, ++u) {
+                unsigned char* x1 = smem + kSwOffX + (u & 1) * 2 * kATile;
+                unsigned char* x2 = x1 + kATile;
+#pragma unroll 1
+                for (int qt = 0; qt < 4; ++qt, ++ch) {  // rows 32 qt .. 32 qt + 31 of the block
+                    const int slot = ch % kSwRing;
+                    const float* stage = reinterpret_cast<const float*>(smem + slot * kSwChunk);
+                    if (tid == 0 && qt == 0) ax_stamp(a.trace, 0, ns);  // waiting for the block's first chunk
+                    mbar_wait(mbar_tma + slot, (ch / kSwRing) & 1);
+                    if (tid == 0 && qt == 0) ax_stamp(a.trace, 0, ns);  // landed
+                    float4 v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(stage + (q * kSwCompute + tid) * 4);
+                    // scale before the barrier: the multiplications consume the loaded registers, so the LDS have really
+                    // returned when the slot is released to the next TMA load (see the tile kernel)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float sc = s_scale[qt * kSwChunkRows + ((q * kSwCompute + tid) >> 5)];
+                        v[q].x *= sc, v[q].y *= sc, v[q].z *= sc, v[q].w *= sc;
+                        asm volatile("" ::"f"(v[q].x), "f"(v[q].y), "f"(v[q].z), "f"(v[q].w));  // (pins the products in front of the barrier)
+                    }
+                    named_bar_sync(3, kSwCompute);  // ring slot drained
+                    if (tid == 0) {
+                        issue_load();      // the chunk three further on, into this slot
+                        issue_prefetch();  // three blocks ahead -> L2
+                    }
+                    if (qt == 0) {
+                        if (u >= 2) mbar_wait(mbar_mma + (u & 1), ((u - 2) >> 1) & 1);  // MMAs of block u - 2 complete: X[u & 1] free
+                        if (tid == 0) ax_stamp(a.trace, 0, ns);  // operand set free
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int f = q * kSwCompute + tid;
+                        const int h = qt * kSwChunkRows + (f >> 5), w = (f & 31) << 2;
+                        __half2 hi[2], lo[2];
+                        sw_split_raw2(v[q].x, v[q].y, hi[0], lo[0]);
+                        sw_split_raw2(v[q].z, v[q].w, hi[1], lo[1]);
+                        const uint32_t off = ax_tile_off(h, w);
+                        *reinterpret_cast<uint2*>(x1 + off) = *reinterpret_cast<uint2*>(hi);
+                        *reinterpret_cast<uint2*>(x2 + off) = *reinterpret_cast<uint2*>(lo);
+                    }
+                }
+                fence_proxy_async();
+                ax_fence_before();
+                named_bar_arrive(1 + (u & 1), kSwCompute + 32);  // -> MMAs of block u
+                if (tid == 0) ax_stamp(a.trace, 0, ns);  // block u converted
+            }
+        }
+    }
+    ax_fence_before();
+    __syncthreads();
+    if (warp == kSwComputeWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -441,6 +789,7 @@ int launch_axis(const float* in, float* out, const float* rowmax_in, float* rowm
     BGAN_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev) {
         BGAN_CUDA_OK(cudaFuncSetAttribute(blur_axis_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kASmem)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_axis_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSwSmem)));
         attr_dev = dev;
     }
     AxisArgs a{};
@@ -457,14 +806,40 @@ int launch_axis(const float* in, float* out, const float* rowmax_in, float* rowm
     a.std_eff = std_eff;
     a.radius = radius;
     a.taps_dev = taps_dev;
+    const char* tr = getenv("BGAN_AXIS_TRACE_PTR");  // debug only: device pointer (decimal) to 768 int64
+    a.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr;
     const int64_t n_tiles = static_cast<int64_t>(planes) * a.tiles_i * a.tiles_j;
     BGAN_REQUIRE(n_tiles < (int64_t(1) << 28), BGAN_E_BADARG, "blur_axis: too many tiles");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(static_cast<unsigned>(std::min<int64_t>(n_tiles, device_sm_count())));
     cfg.blockDim = dim3(kAxCta);
     cfg.dynamicSmemBytes = kASmem;
     cfg.stream = stream;
+    const char* no_sweep = getenv("BGAN_BLUR_AXIS_NO_SWEEP");
+    if (a.nb == 1 && a.tiles_j >= 2 && !(no_sweep && atoi(no_sweep))) {
+        SweepMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        const cuuint32_t box_in[3] = {kB, kSwChunkRows, 1};
+        CUresult r2 = axis_encode_fn()(&maps.in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(in), dims, strides, box_in, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        BGAN_REQUIRE(r2 == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled (sweep input) failed (%d)", static_cast<int>(r2));
+        const cuuint64_t odims[3] = {static_cast<cuuint64_t>(I), static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(planes)};
+        const cuuint64_t ostrides[2] = {static_cast<cuuint64_t>(I) * 4, static_cast<cuuint64_t>(K) * I * 4};
+        const cuuint32_t box_out[3] = {32, kB, 1};
+        r2 = axis_encode_fn()(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, odims, ostrides, box_out, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        BGAN_REQUIRE(r2 == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled (sweep output) failed (%d)", static_cast<int>(r2));
+        // strips of 128 input rows; balanced persistent grid (every CTA the same number of strips where possible)
+        const int64_t strips = static_cast<int64_t>(planes) * a.tiles_i;
+        const int64_t rounds = ceil_div64(strips, device_sm_count());
+        cfg.gridDim = dim3(static_cast<unsigned>(ceil_div64(strips, rounds)));
+        cfg.blockDim = dim3(kSwCta);
+        cfg.dynamicSmemBytes = kSwSmem;
+        BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_axis_sweep_kernel, a, maps));
+        return 0;
+    }
+    cfg.gridDim = dim3(static_cast<unsigned>(std::min<int64_t>(n_tiles, device_sm_count())));
     BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_axis_tc_kernel, a, tmap));
     return 0;
 }

@@ -7,6 +7,10 @@
 //   scatter : stable rank inside the tile (lanes with equal digits found by eight ballots -- match_any for the top
 //             byte, which takes few distinct values -- plus per-warp counters), keys regrouped by
 //             digit in shared memory, then written as coalesced runs to their global positions.
+// A "one sweep" variant (all four histograms from one read of the keys, decoupled look-back in the scatter: 36 instead of
+// 48 bytes per key) was built and measured in round 2 and is NOT here: the histogram is bound by shared-memory atomics
+// (3 per key: 365 us against 4 x 135 us for the per-pass kernels), the look-back scatter took 520 - 560 us per pass
+// against ~400, 54 instead of 61 Gkeys/s at 512 x 262144 keys (profiles/r02_sort.md).
 // Tile = 256 threads x 16 keys.  The float<->uint transform is fused into the first load and the
 // last store, so the sort runs in place from the caller's point of view (ping-pong through ws).
 #include <algorithm>

@@ -151,6 +151,28 @@ def test_large_image_wide_halo(std, monkeypatch):
     assert ops.last_blur_path() in (1, 2, 3)
 
 
+@pytest.mark.parametrize("shape,std,no_sweep", [((40, 1, 1024, 256), 20.0, 0), ((40, 1, 256, 1024), 7.0, 0), ((24, 1, 512, 512), 12.0, 1),
+                                                 ((5, 1, 1024, 1024), 64.0, 0)])
+def test_axis_tensor_core_path_many_work_units_per_cta(shape, std, no_sweep, monkeypatch):
+    """Persistent CTAs that take several strips (sweep kernel, radius <= 128: 320 strips on 107 CTAs in the first pass of the
+    first case) or several tiles (tile kernel: radius > 128, or the sweep switched off) in a row: the hand-over of row scales,
+    accumulator slots and operand buffers from one work unit to the next.  Every plane is checked, the planes have different
+    magnitudes, and the TF rule at std 64 has radius 192 (nb = 2)."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import blur_images
+
+    if no_sweep:
+        monkeypatch.setenv("BGAN_BLUR_AXIS_NO_SWEEP", "1")
+    x = uniform_pm1(77, shape)
+    x *= (10.0 ** np.random.RandomState(3).uniform(-4, 2, size=(shape[0], 1, 1, 1))).astype(np.float32)
+    want = bo.blur_images_tf_ref(np.ascontiguousarray(x.transpose(0, 2, 3, 1)), std).transpose(0, 3, 1, 2)
+    # (NCHW input of more than 3 channels-last... the functional entry point sees a 4-D tensor whose last dim is not 1 or 3: NCHW)
+    got = blur_images(_dev(x), std)
+    assert ops.last_blur_path() == 6
+    for n in range(shape[0]):
+        assert_close(got[n], want[n], "plane %d of %s std=%g" % (n, shape, std))
+
+
 @pytest.mark.parametrize("shape,std", [((2, 1, 256, 256), 6.0), ((1, 3, 300, 260), 9.0), ((1, 2, 512, 384), 40.0), ((3, 1, 260, 516), 20.0)])
 def test_axis_tensor_core_path_ragged_planes(shape, std):
     """Planes that are not multiples of the 128 x 128 tile, both tap rules, forward and backward, asymmetric explicit taps."""

@@ -43,11 +43,14 @@ for s in [float(v) for v in args.stds.split(",")]:
     ms = e0.elapsed_time(e1) / args.iters
     line = "std %5.1f taps %3d path %d: %.4f ms per launch, %.1f images/s, %.1f GB/s algorithmic = %.3f of %.1f" % (
         s, 2 * radius + 1, lib.bgan_blur2d_last_path(), ms, N / (ms * 1e-3), nbytes / (ms * 1e-3) / 1e9, nbytes / (ms * 1e-3) / 1e9 / peak, peak)
-    if args.check:
+    if args.check:  # first, middle and last plane against the CPU oracle
         from oracle import blur_oracle as bo
-        xh = np.ascontiguousarray(xs[0][:1, :1].permute(0, 2, 3, 1).cpu().numpy())
-        want = bo.blur_images_tf_ref(xh, s)[0, :, :, 0]
         go(0)
-        got = ys[0][0, 0].cpu().numpy()
-        line += "  err %.2e" % (np.abs(got - want).max() / np.abs(want).max())
+        errs = []
+        for n, c in ((0, 0), (N // 2, 1), (N - 1, C - 1)):
+            xh = np.ascontiguousarray(xs[0][n : n + 1, c : c + 1].permute(0, 2, 3, 1).cpu().numpy())
+            want = bo.blur_images_tf_ref(xh, s)[0, :, :, 0]
+            got = ys[0][n, c].cpu().numpy()
+            errs.append(np.abs(got - want).max() / np.abs(want).max())
+        line += "  err %s" % " ".join("%.2e" % e for e in errs)
     print(line, flush=True)

@@ -52,7 +52,7 @@ def run(sync_ops):
 run(False)
 total, phases, res = run(False)
 print("eval %.4f s" % total, {k: round(v, 4) for k, v in phases.items()}, np.round(res, 4).tolist())
-for name in ("swd_project", "swd_sort_", "swd_absdiff_sum", "swd_normalise_", "swd_extract", "pyr_down", "pyr_up"):
+for name in ("swd_project", "swd_sort_", "swd_sort_diff_", "swd_absdiff_sum", "swd_normalise_", "swd_feed", "swd_extract", "pyr_down", "pyr_up"):
     timed(ops, name)
 timed(bd, "positions_packed_for_round")
 timed(bd, "all_gather_rows")
