@@ -69,7 +69,9 @@ size_t bgan_blur2d_workspace_bytes(int n, int c, int height, int width, int layo
  * Replaces GaussianBlur.forward (pytorch/gaussianblur.py:59-71), gaussian_blur()
  * (gaussian_blur.py:91-132) and -- B being self-adjoint -- their autograd backward and
  * double-backward (call sites wgan.py:140,166,244): backward is the same call on grad_output.
- * x and y are device pointers to N*C*H*W floats in `layout`; x == y is NOT allowed. */
+ * x and y are device pointers to N*C*H*W floats in `layout`; x == y is NOT allowed.
+ * Non-finite inputs: an Inf / NaN pixel contaminates its tap neighbourhood on the FFMA paths (1, 2, 3, 5), like the reference's
+ * convolution, and its whole plane on the tensor-core paths (4, 6, 7: 0 x NaN inside the MMAs); other planes are unaffected. */
 int bgan_blur2d_f32(const float* x_device, float* y_device, int n, int c, int height, int width, int layout,
                     int rule, float std_eff, int radius, const float* taps_device,
                     void* ws_device, size_t ws_bytes, void* stream);

@@ -117,6 +117,31 @@ def test_ragged_shapes_both_rules(shape, layout):
             assert_close(GaussianBlur(std).cuda()(_dev(x)), bo.gaussian_blur_torch_ref(x, std), "torch %s std=%g" % (shape, std))
 
 
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_non_finite_pixel_stays_in_its_plane(bad):
+    """what an Inf / NaN pixel does depends on the kernel -- its tap neighbourhood on the FFMA path (like the
+    reference's convolution), its whole plane on the tensor-core path (0 x NaN inside the MMAs) -- but it never leaves its plane."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
+
+    x = uniform_pm1(8, (2, 3, 128, 128))
+    clean = x.copy()
+    x[0, 1, 40, 77] = bad
+    for std, path in ((0.5, 5), (5.0, 4)):
+        y = GaussianBlur(std).cuda()(_dev(x)).cpu().numpy()
+        assert ops.last_blur_path() == path
+        want = bo.gaussian_blur_torch_ref(clean, std)
+        assert not np.isfinite(y[0, 1, 40, 77])
+        for n in range(2):
+            for c in range(3):
+                if (n, c) != (0, 1):
+                    assert np.isfinite(y[n, c]).all()
+                    assert_close(y[n, c], want[n, c], "plane (%d, %d) next to a non-finite one, std=%g" % (n, c, std))
+        if path == 5:  # FFMA: only the (2r + 1)^2 neighbourhood (radius 1 at std 0.5)
+            finite = np.isfinite(y[0, 1])
+            assert (~finite).sum() <= 9 and finite[:38].all() and finite[43:].all()
+
+
 @pytest.mark.parametrize("std", [8.0, 32.0, 64.0])
 def test_large_image_wide_halo(std, monkeypatch):
     """BASELINE configs[3] shape (1024 x 1024, std up to 64), reduced batch for the CPU oracle.  NCHW planes run on the
