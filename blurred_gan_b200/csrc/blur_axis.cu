@@ -18,12 +18,14 @@
 // order and the epilogue multiplies by 2^-11 / scale_i.  K-steps of a neighbouring block that only meet zeros of T are
 // neither converted nor issued.
 //
-// Two schedules (template parameter SWEEP), one set of roles -- 8 conversion warps, the MMA-issuing warp, 8 store warps:
-//   SWEEP (radius <= 128): input-stationary.  A CTA takes a strip (128 input rows of a plane) and walks the blocks along
-//     the blurred axis; every block is loaded and converted ONCE and multiplied into the up to three output tiles it touches
-//     (J = L - 1, which it completes, L, and L + 1, which it starts).  Four accumulator slots: three live, one draining.
-//   tiles (radius 129 .. 256): output-stationary.  Five live accumulators per strip would need 640 TMEM columns, so a CTA
-//     takes output tiles and loads the up to five blocks of each; the four slots let the store warps lag three tiles.
+// Schedule, one set of roles -- 8 conversion warps, the MMA-issuing warp, 8 store warps.  A work unit is a run of adjacent
+// output tiles J0 .. J0 + nt - 1 of one strip (128 input rows i of a plane); the CTA walks the input blocks L that the band
+// reaches from those tiles, loads and converts every block ONCE and multiplies it into every tile of the unit with
+// |L - J| <= nb.  Four accumulator slots of 128 TMEM columns:
+//   radius <= 128 (nb = 1): the unit is the whole strip (input-stationary sweep): a block touches J = L - 1 (which it
+//     completes), L and L + 1 (which it starts) -- three live accumulators, one draining; every block crosses L2 -> SM once.
+//   radius 129 .. 256 (nb = 2): a whole strip would need five live accumulators (640 TMEM columns), so units are PAIRS of
+//     tiles (two live, two draining): six block loads per two tiles instead of five per tile.
 // What the measurements said on the way (profiles/r02_axis.md): round 1's kernel loaded every block once per tile with one
 // 64 KB TMA box in flight (a latency chain: DRAM 13 %, tensor pipe 18 %); direct stores of accumulator rows are 32 lines per
 // instruction, 4096 sixteen-byte requests per tile, which paced the kernel and starved the conversion warps' LDS / STS in the
@@ -62,13 +64,13 @@ constexpr uint32_t kAIdesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 2
 constexpr int kARev = 0x78;
 
 // Shared memory: ring | X[2][hi | lo] | two output boxes | strips hi, lo | scales, barriers.
-//   SWEEP: output boxes of 32 columns (128 rows x 128 B, SWIZZLE_128B), strips of 63 core matrices
-//   tiles: output boxes of 16 columns (128 rows x 64 B, SWIZZLE_64B), strips of 95 core matrices
-template <bool SWEEP>
+//   nb = 1: output boxes of 32 columns (128 rows x 128 B, SWIZZLE_128B), strips of 63 core matrices
+//   nb = 2 (WIDE): output boxes of 16 columns (128 rows x 64 B, SWIZZLE_64B), strips of 95 core matrices
+template <bool WIDE>
 struct AxLayout {
-    static constexpr int kBoxCols = SWEEP ? 32 : 16;
+    static constexpr int kBoxCols = WIDE ? 16 : 32;
     static constexpr uint32_t kBox = kB * kBoxCols * 4;
-    static constexpr uint32_t kStrip = SWEEP ? 8192 : 12288;  // (32 nb + 31) x 128 B, nb = 1 / 2
+    static constexpr uint32_t kStrip = WIDE ? 12288 : 8192;  // (32 nb + 31) x 128 B
     static constexpr uint32_t kOffRing = 0;
     static constexpr uint32_t kOffX = kAxRing * kAxChunk;      // the raw taps live here until the first conversion
     static constexpr uint32_t kOffOut = kOffX + 4 * kATile;
@@ -84,6 +86,8 @@ struct AxisArgs {
     float* rowmax_out;        // [planes][K] or nullptr: max |out| over each output row (accumulated with atomicMax)
     int I, K, planes;
     int tiles_i, tiles_j;
+    int unit_tiles;           // output tiles per work unit (nb = 1: tiles_j, the whole strip; nb = 2: 2)
+    int units_per_strip;      // ceil(tiles_j / unit_tiles)
     int nb;                   // ceil(radius / 128)
     int rule;
     float std_eff;
@@ -220,33 +224,28 @@ __device__ __forceinline__ void ks_range(int d, int radius, int& k0, int& k1) {
     if (d > 0) k1 = min(7, (radius - 1 - (d - 1) * kB) >> 4);
 }
 
-// A work unit: SWEEP: strip = (plane, ib), blocks L = 0 .. tiles_j - 1, finishes tiles_j tiles;
-//              tiles: (plane, ib, jb), blocks d = b0 .. b1 (input block jb + d, inside the array), finishes one tile.
+// A work unit: output tiles J0 .. J0 + nt - 1 of strip (plane, ib); input blocks L0 .. L1 (those the band reaches, inside the array)
 struct Unit {
-    int plane, ib, jb, b0, b1;
+    int plane, ib, J0, nt, L0, L1;
 };
-template <bool SWEEP>
 __device__ __forceinline__ Unit unit_of(const AxisArgs& a, int idx) {
     Unit u;
-    if (SWEEP) {
-        u.plane = idx / a.tiles_i;
-        u.ib = idx - u.plane * a.tiles_i;
-        u.jb = 0;
-        u.b0 = 0;
-        u.b1 = a.tiles_j - 1;
-    } else {
-        u.jb = idx % a.tiles_j;
-        u.ib = (idx / a.tiles_j) % a.tiles_i;
-        u.plane = idx / (a.tiles_j * a.tiles_i);
-        u.b0 = -min(a.nb, u.jb);
-        u.b1 = min(a.nb, a.tiles_j - 1 - u.jb);
-    }
+    const int g = idx % a.units_per_strip, strip = idx / a.units_per_strip;
+    u.plane = strip / a.tiles_i;
+    u.ib = strip - u.plane * a.tiles_i;
+    u.J0 = g * a.unit_tiles;
+    u.nt = min(a.unit_tiles, a.tiles_j - u.J0);
+    u.L0 = max(0, u.J0 - a.nb);
+    u.L1 = min(a.tiles_j - 1, u.J0 + u.nt - 1 + a.nb);
     return u;
 }
+// first / last input block that contributes to output tile J
+__device__ __forceinline__ int first_block(const AxisArgs& a, int J) { return max(0, J - a.nb); }
+__device__ __forceinline__ int last_block(const AxisArgs& a, int J) { return min(a.tiles_j - 1, J + a.nb); }
 
-template <bool SWEEP>
+template <bool WIDE>
 __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, const __grid_constant__ AxisMaps maps) {
-    using L = AxLayout<SWEEP>;
+    using L = AxLayout<WIDE>;
     extern __shared__ __align__(1024) unsigned char smem[];
     float* s_g = reinterpret_cast<float*>(smem + L::kOffX);         // taps (<= 513), only until the strip is built
     float* s_scale = reinterpret_cast<float*>(smem + L::kOffMisc);  // [128] per input row of the unit being converted
@@ -262,8 +261,7 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int first = blockIdx.x, stride = gridDim.x;
-    const int n_units = SWEEP ? a.planes * a.tiles_i : a.planes * a.tiles_i * a.tiles_j;
-    const int tiles_per_unit = SWEEP ? a.tiles_j : 1;
+    const int n_units = a.planes * a.tiles_i * a.units_per_strip;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
@@ -323,43 +321,33 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
                 ax_mma(acc, a2 + k * 16, b1 + ax_kstep(k), 1);
             }
         };
-        for (int idx = first; idx < n_units; idx += stride, base += tiles_per_unit) {
-            const Unit un = unit_of<SWEEP>(a, idx);
-            for (int b = un.b0; b <= un.b1; ++b, ++u) {
+        for (int idx = first; idx < n_units; idx += stride) {
+            const Unit un = unit_of(a, idx);
+            for (int Lb = un.L0; Lb <= un.L1; ++Lb, ++u) {
                 named_bar_sync(1 + (u & 1), kAxCompute + 32);  // X[u & 1] of block u written
                 if (lane == 0) {
                     ax_stamp(a.trace, 1, ns);  // block u: operands ready
                     ax_fence_after();
                     const uint32_t xb = sbase + L::kOffX + (u & 1) * 2 * kATile;
                     const uint64_t b1 = ax_desc_sw128(xb), b2 = ax_desc_sw128(xb + kATile);
-                    if (SWEEP) {
-                        const int TJ = a.tiles_j;
+                    // tiles of the unit within reach of the block, the one it completes first
+                    const int Ja = max(un.J0, Lb - a.nb), Jb = min(un.J0 + un.nt - 1, Lb + a.nb);
 #pragma unroll 1
-                        for (int d = 1; d >= -1; --d) {  // tile J = L - d: d = +1 finishes J = L - 1, d = -1 starts J = L + 1
-                            const int J = b - d;
-                            if (J < 0 || J >= TJ) continue;
-                            const int tj = base + J, slot = tj & (kAxSlots - 1);
-                            const bool starts = b == (J > 0 ? J - 1 : 0);
-                            if (starts && tj >= kAxSlots) mbar_wait(mbar_acc_free + slot, ((tj >> 2) - 1) & 1);  // slot drained
-                            if (starts) ax_fence_after();
-                            issue(slot, d, starts, b1, b2);
-                        }
-                        ax_commit(mbar_mma + (u & 1));
-                        if (b >= 1) ax_commit(mbar_acc_full + ((base + b - 1) & (kAxSlots - 1)));  // tile L - 1 complete
-                        if (b == TJ - 1) ax_commit(mbar_acc_full + ((base + b) & (kAxSlots - 1)));  // ... and the last one
-                    } else {
-                        const int tj = base, slot = tj & (kAxSlots - 1);
-                        const bool starts = b == un.b0;
+                    for (int J = Ja; J <= Jb; ++J) {
+                        const int tj = base + (J - un.J0), slot = tj & (kAxSlots - 1);
+                        const bool starts = Lb == first_block(a, J);
                         if (starts && tj >= kAxSlots) mbar_wait(mbar_acc_free + slot, ((tj >> 2) - 1) & 1);  // slot drained
                         if (starts) ax_fence_after();
-                        issue(slot, b, starts, b1, b2);
-                        ax_commit(mbar_mma + (u & 1));
-                        if (b == un.b1) ax_commit(mbar_acc_full + slot);
+                        issue(slot, Lb - J, starts, b1, b2);
                     }
+                    ax_commit(mbar_mma + (u & 1));
+                    for (int J = Ja; J <= Jb; ++J)
+                        if (Lb == last_block(a, J)) ax_commit(mbar_acc_full + ((base + (J - un.J0)) & (kAxSlots - 1)));  // tile J complete
                     ax_stamp(a.trace, 1, ns);  // block u: issued
                 }
                 __syncwarp();
             }
+            base += un.nt;
         }
     } else if (warp > kAxComputeWarps) {
         // ================= store warps: out[j][i] = D 2^-11 / scale_i, through swizzled boxes and TMA stores ===========
@@ -376,11 +364,11 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
         unsigned char* obox = smem + L::kOffOut + box * L::kBox;
         const uint32_t orow = static_cast<uint32_t>(jl) * (BC * 4);
         const uint32_t oxor = BC == 32 ? (jl & 7) : ((jl >> 1) & 3);  // SWIZZLE_128B: chunk ^ (row % 8); SWIZZLE_64B: chunk ^ ((row / 2) % 4)
-        for (int idx = first; idx < n_units; idx += stride, base += tiles_per_unit, ++ul) {
-            const Unit un = unit_of<SWEEP>(a, idx);
+        for (int idx = first; idx < n_units; idx += stride, ++ul) {
+            const Unit un = unit_of(a, idx);
             const float* inv = s_inv + (ul & 3) * kB;
-            for (int t = 0; t < tiles_per_unit; ++t) {
-                const int J = SWEEP ? t : un.jb;
+            for (int t = 0; t < un.nt; ++t) {
+                const int J = un.J0 + t;
                 const int tj = base + t, slot = tj & (kAxSlots - 1);
                 mbar_wait(mbar_acc_full + slot, (tj >> 2) & 1);
                 ax_fence_after();
@@ -420,6 +408,7 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
                     atomicMax(reinterpret_cast<int*>(a.rowmax_out + static_cast<size_t>(un.plane) * a.K + j), __float_as_int(mx));
                 if (issuer) ax_stamp(a.trace, 2, ns);  // tile handed to the TMA
             }
+            base += un.nt;
             __syncwarp();
             if (lane == 0) mbar_arrive(mbar_unit_done + (ul & 3));  // s_inv[ul & 3] may be replaced (four units on)
         }
@@ -428,28 +417,28 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
         // ================= conversion warps ===========================================================
         // thread 0 walks the chunks (32 rows of a block): next one to load into the ring / to pull into L2 (further ahead)
         struct Cursor {
-            int idx, b, q;
+            int idx, Lb, q;
             Unit un;
         };
         Cursor ld{}, pf{};
         int ld_c = 0;  // chunks issued
         auto init = [&](Cursor& c) {
             c.idx = first;
-            c.un = unit_of<SWEEP>(a, min(first, n_units - 1));
-            c.b = c.un.b0;
+            c.un = unit_of(a, min(first, n_units - 1));
+            c.Lb = c.un.L0;
             c.q = 0;
         };
         auto advance = [&](Cursor& c) {
             if (++c.q < 4) return;
             c.q = 0;
-            if (++c.b <= c.un.b1) return;
+            if (++c.Lb <= c.un.L1) return;
             c.idx += stride;
             if (c.idx < n_units) {
-                c.un = unit_of<SWEEP>(a, c.idx);
-                c.b = c.un.b0;
+                c.un = unit_of(a, c.idx);
+                c.Lb = c.un.L0;
             }
         };
-        auto k_coord = [&](const Cursor& c) { return (SWEEP ? c.b : c.un.jb + c.b) * kB; };
+        auto k_coord = [&](const Cursor& c) { return c.Lb * kB; };
         auto issue_load = [&]() {
             if (ld.idx >= n_units) return;
             const int slot = ld_c % kAxRing;
@@ -472,7 +461,7 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
         int u = 0, ul = 0, ch = 0;  // blocks, units, chunks consumed
         int ns = 0;
         for (int idx = first; idx < n_units; idx += stride, ++ul) {
-            const Unit un = unit_of<SWEEP>(a, idx);
+            const Unit un = unit_of(a, idx);
             named_bar_sync(3, kAxCompute);  // every warp has converted the previous unit's last block: s_scale may change
             if (ul >= 4) mbar_wait(mbar_unit_done + (ul & 3), ((ul >> 2) - 1) & 1);  // s_inv[ul & 3] no longer read
             if (tid < kB) {
@@ -484,10 +473,15 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
                 s_inv[(ul & 3) * kB + tid] = __int_as_float((eb - 12) << 23);
             }
             named_bar_sync(3, kAxCompute);
-            for (int b = un.b0; b <= un.b1; ++b, ++u) {
-                // columns of the block that some tile needs: SWEEP: all (the block is the centre of tile L); tiles: its K-steps
-                int k0 = 0, k1 = 7;
-                if (!SWEEP) ks_range(b, a.radius, k0, k1);
+            for (int Lb = un.L0; Lb <= un.L1; ++Lb, ++u) {
+                // columns of the block that some tile of the unit needs (all of them when the block is a tile's centre)
+                int k0 = 8, k1 = -1;
+                for (int J = max(un.J0, Lb - a.nb); J <= min(un.J0 + un.nt - 1, Lb + a.nb); ++J) {
+                    int ka, kb;
+                    ks_range(Lb - J, a.radius, ka, kb);
+                    k0 = min(k0, ka);
+                    k1 = max(k1, kb);
+                }
                 const int w_lo = 16 * k0, w_hi = 16 * k1 + 16;
                 unsigned char* x1 = smem + L::kOffX + (u & 1) * 2 * kATile;
                 unsigned char* x2 = x1 + kATile;
@@ -525,7 +519,7 @@ __global__ void __launch_bounds__(kAxCta, 1) blur_axis_kernel(const AxisArgs a, 
                     for (int q = 0; q < 4; ++q) {
                         const int f = q * kAxCompute + tid;
                         const int h = qt * kAxChunkRows + (f >> 5), w = (f & 31) << 2;
-                        if (SWEEP || (w >= w_lo && w < w_hi)) {
+                        if (w >= w_lo && w < w_hi) {
                             __half2 hi[2], lo[2];
                             ax_split_raw2(v[q].x, v[q].y, hi[0], lo[0]);
                             ax_split_raw2(v[q].z, v[q].w, hi[1], lo[1]);
@@ -562,9 +556,9 @@ EncodeTiledFn axis_encode_fn() {
     return fn;
 }
 
-template <bool SWEEP>
+template <bool WIDE>
 int launch_axis_mode(const AxisArgs& a, const float* in, float* out, int planes, int I, int K, int64_t units, cudaStream_t stream) {
-    using L = AxLayout<SWEEP>;
+    using L = AxLayout<WIDE>;
     AxisMaps maps;
     memset(&maps, 0, sizeof(maps));
     const cuuint32_t estr[3] = {1, 1, 1};
@@ -579,14 +573,14 @@ int launch_axis_mode(const AxisArgs& a, const float* in, float* out, int planes,
     const cuuint64_t ostrides[2] = {static_cast<cuuint64_t>(I) * 4, static_cast<cuuint64_t>(K) * I * 4};
     const cuuint32_t box_out[3] = {static_cast<cuuint32_t>(L::kBoxCols), kB, 1};
     res = axis_encode_fn()(&maps.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, odims, ostrides, box_out, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           SWEEP ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           WIDE ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     BGAN_REQUIRE(res == CUDA_SUCCESS, BGAN_E_UNSUPPORTED, "cuTensorMapEncodeTiled (axis output) failed (%d)", static_cast<int>(res));
     thread_local int attr_dev = -1;
     int dev = 0;
     BGAN_CUDA_OK(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_axis_kernel<SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kSmem)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(blur_axis_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kSmem)));
         attr_dev = dev;
     }
     cudaLaunchConfig_t cfg;
@@ -597,7 +591,7 @@ int launch_axis_mode(const AxisArgs& a, const float* in, float* out, int planes,
     cfg.blockDim = dim3(kAxCta);
     cfg.dynamicSmemBytes = L::kSmem;
     cfg.stream = stream;
-    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_axis_kernel<SWEEP>, a, maps));
+    BGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, blur_axis_kernel<WIDE>, a, maps));
     return 0;
 }
 
@@ -626,10 +620,15 @@ int launch_axis(const float* in, float* out, const float* rowmax_in, float* rowm
     a.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 10)) : nullptr;
     const int64_t n_tiles = static_cast<int64_t>(planes) * a.tiles_i * a.tiles_j;
     BGAN_REQUIRE(n_tiles < (int64_t(1) << 28), BGAN_E_BADARG, "blur_axis: too many tiles");
-    const char* no_sweep = getenv("BGAN_BLUR_AXIS_NO_SWEEP");
-    if (a.nb == 1 && a.tiles_j >= 2 && !(no_sweep && atoi(no_sweep)))
-        return launch_axis_mode<true>(a, in, out, planes, I, K, static_cast<int64_t>(planes) * a.tiles_i, stream);
-    return launch_axis_mode<false>(a, in, out, planes, I, K, n_tiles, stream);
+    // work units: whole strips for radius <= 128, pairs of tiles above (BGAN_BLUR_AXIS_UNIT_TILES overrides: experiments / tests)
+    a.unit_tiles = a.nb == 1 ? a.tiles_j : 2;
+    if (const char* ut = getenv("BGAN_BLUR_AXIS_UNIT_TILES")) {
+        if (atoi(ut) > 0) a.unit_tiles = std::min(atoi(ut), a.nb == 1 ? a.tiles_j : 2);
+    }
+    a.units_per_strip = ceil_div(a.tiles_j, a.unit_tiles);
+    const int64_t units = static_cast<int64_t>(planes) * a.tiles_i * a.units_per_strip;
+    if (a.nb == 1) return launch_axis_mode<false>(a, in, out, planes, I, K, units, stream);
+    return launch_axis_mode<true>(a, in, out, planes, I, K, units, stream);
 }
 
 }  // namespace

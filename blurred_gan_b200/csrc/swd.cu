@@ -93,6 +93,48 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(const float* __restrict__ x
     }
 }
 
+// pyr_up for 2h, 2w >= 3: one thread per source pixel (a, b) computes the 2 x 2 output quad (2a .. 2a + 1, 2b .. 2b + 1) from
+// the 3 x 3 source neighbourhood.  Zero stuffing leaves an even output row the source rows a - 1, a, a + 1 with weights
+// 1, 6, 1 and an odd one the rows a, a + 1 with weights 4, 4 (columns alike); REFLECT_101 on the zero-stuffed grid keeps the
+// parity of an index, so at the borders row -1 becomes row 1 and row h becomes row h - 1.  Same products, same exact fp64
+// sums, hence the same bits as pyr_up_kernel -- with 9 loads per four outputs instead of ~25, and 8-byte stores.
+__global__ void __launch_bounds__(256) pyr_up_quad_kernel(const float* __restrict__ x, const float* __restrict__ minuend, float* __restrict__ y,
+                                                          int planes, int h, int w) {
+    const unsigned total = static_cast<unsigned>(planes) * h * w;
+    const int OW = 2 * w;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned r = idx / static_cast<unsigned>(w);
+        const int b = static_cast<int>(idx - r * w);
+        const unsigned p = r / static_cast<unsigned>(h);
+        const int a = static_cast<int>(r - p * h);
+        const float* src = x + static_cast<size_t>(p) * h * w;
+        const int rows[3] = {a == 0 ? 1 : a - 1, a, a + 1 < h ? a + 1 : h - 1};
+        const int cols[3] = {b == 0 ? 1 : b - 1, b, b + 1 < w ? b + 1 : w - 1};
+        double he[3], ho[3];  // per source row: horizontal sums for the even / odd output column
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float* row = src + static_cast<size_t>(rows[i]) * w;
+            const double s0 = static_cast<double>(__ldg(row + cols[0])), s1 = static_cast<double>(__ldg(row + cols[1])),
+                         s2 = static_cast<double>(__ldg(row + cols[2]));
+            he[i] = s0 + 6.0 * s1 + s2;
+            ho[i] = 4.0 * s1 + 4.0 * s2;
+        }
+        const float ee = static_cast<float>((he[0] + 6.0 * he[1] + he[2]) * (4.0 / 256.0));
+        const float eo = static_cast<float>((ho[0] + 6.0 * ho[1] + ho[2]) * (4.0 / 256.0));
+        const float oe = static_cast<float>((4.0 * he[1] + 4.0 * he[2]) * (4.0 / 256.0));
+        const float oo = static_cast<float>((4.0 * ho[1] + 4.0 * ho[2]) * (4.0 / 256.0));
+        const size_t o0 = (static_cast<size_t>(p) * 2 * h + 2 * a) * OW + 2 * b, o1 = o0 + OW;
+        float2 top = make_float2(ee, eo), bot = make_float2(oe, oo);
+        if (minuend) {
+            const float2 m0 = __ldg(reinterpret_cast<const float2*>(minuend + o0)), m1 = __ldg(reinterpret_cast<const float2*>(minuend + o1));
+            top = make_float2(m0.x - ee, m0.y - eo);
+            bot = make_float2(m1.x - oe, m1.y - oo);
+        }
+        *reinterpret_cast<float2*>(y + o0) = top;
+        *reinterpret_cast<float2*>(y + o1) = bot;
+    }
+}
+
 // desc[m, c, i, j] = level[m / per_image, c, py[m] + j - half, px[m] + i - half]; per-channel sum / sum-of-squares.
 // One warp per descriptor (grid-stride): the lanes walk the C * nhood^2 floats of the descriptor, so the output row is
 // written coalesced.  The descriptor geometry does not depend on the descriptor: every lane computes the image offsets and
@@ -102,9 +144,9 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(const float* __restrict__ x
 // the global sums: six atomics per CTA on a grid of at most two CTAs per SM (one atomic per warp and statistic made this
 // kernel 75 us per minibatch; 1024 CTAs x 6 atomics on six addresses still 12.8 us, most of it the serialised L2 atomics).
 template <int MAXC, int SLOTS>
-__global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ level, int C, int h, int w, const int32_t* __restrict__ px,
-                                                      const int32_t* __restrict__ py, int per_image, int nhood, int64_t n_desc,
-                                                      float* __restrict__ out, double* __restrict__ sums) {
+__device__ __forceinline__ void extract_body(const float* __restrict__ level, int C, int h, int w, const int32_t* __restrict__ px,
+                                             const int32_t* __restrict__ py, int per_image, int nhood, int64_t n_desc, float* __restrict__ out,
+                                             double* __restrict__ sums) {
     __shared__ double s_part[8][2 * MAXC];
     const int half = nhood / 2;
     const int per_chan = nhood * nhood;
@@ -174,6 +216,30 @@ __global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ 
             atomicAdd(sums + which * C + c, t);
         }
     }
+}
+
+template <int MAXC, int SLOTS>
+__global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ level, int C, int h, int w, const int32_t* __restrict__ px,
+                                                      const int32_t* __restrict__ py, int per_image, int nhood, int64_t n_desc,
+                                                      float* __restrict__ out, double* __restrict__ sums) {
+    extract_body<MAXC, SLOTS>(level, C, h, w, px, py, per_image, nhood, n_desc, out, sums);
+}
+
+// The gathers of all pyramid levels of one `feed` as ONE launch (blockIdx.y = level): four launches of 8192 descriptors each
+// are latency-bound (7.5 us each: a warp walks its descriptors one after the other), one launch has four times the warps in
+// flight.  The levels' residuals all live in the feed workspace until the end of the call.
+constexpr int kMaxFeedLevels = 8;
+struct ExtractLevels {
+    const float* level[kMaxFeedLevels];
+    const int32_t* px[kMaxFeedLevels];
+    float* out[kMaxFeedLevels];
+    double* sums[kMaxFeedLevels];
+    int h[kMaxFeedLevels], w[kMaxFeedLevels];
+};
+template <int MAXC, int SLOTS>
+__global__ void __launch_bounds__(256) extract_levels_kernel(const ExtractLevels lv, int C, int per_image, int nhood, int64_t n_desc) {
+    const int l = blockIdx.y;
+    extract_body<MAXC, SLOTS>(lv.level[l], C, lv.h[l], lv.w[l], lv.px[l], lv.px[l] + n_desc, per_image, nhood, n_desc, lv.out[l], lv.sums[l]);
 }
 
 // desc = (desc - mean_c) / std_c, two fp32 operations like numpy's in-place `-=` then `/=` (a true IEEE division).
@@ -362,7 +428,11 @@ extern "C" int bgan_pyr_up_f32(const float* x, const float* minuend, float* y, i
     BGAN_REQUIRE(x && y && planes > 0 && h > 0 && w > 0, BGAN_E_BADARG, "bgan_pyr_up_f32: bad arguments");
     const int64_t total = static_cast<int64_t>(planes) * 4 * h * w;
     BGAN_REQUIRE(total < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_pyr_up_f32: more than 2^31 pixels per call");
-    pyr_up_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, minuend, y, planes, h, w);
+    const bool aligned8 = reinterpret_cast<uintptr_t>(y) % 8 == 0 && (minuend == nullptr || reinterpret_cast<uintptr_t>(minuend) % 8 == 0);
+    if (h >= 2 && w >= 2 && aligned8)
+        pyr_up_quad_kernel<<<grid_for(total / 4, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, minuend, y, planes, h, w);
+    else
+        pyr_up_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, minuend, y, planes, h, w);
     BGAN_LAUNCH_OK();
     return 0;
 }
@@ -417,6 +487,9 @@ extern "C" int bgan_swd_feed_f32(const float* minibatch, int n, int c, int h, in
         BGAN_REQUIRE(desc_out[l] && sums[l], BGAN_E_BADARG, "bgan_swd_feed_f32: null output for level %d", l);
     }
     const int64_t count = static_cast<int64_t>(n) * nhoods_per_image;
+    const int dlen = c * nhood * nhood;
+    const bool fused_gather = levels <= kMaxFeedLevels && dlen <= 32 * 5 && c <= 4 && (nhood & 1) && nhoods_per_image > 0;
+    ExtractLevels lv{};
     float* next = static_cast<float*>(ws);
     const float* cur = minibatch;  // Gaussian image of the current level
     int hl = h, wl = w;
@@ -436,10 +509,25 @@ extern "C" int bgan_swd_feed_f32(const float* minibatch, int n, int c, int h, in
             level = resid;
             cur = coarse;
         }
-        const int rc = bgan_swd_extract_f32(level, n, c, hl, wl, px, py, nhoods_per_image, nhood, desc_out[l], sums[l], stream);  // :13-23
-        if (rc) return rc;
+        BGAN_REQUIRE(hl >= nhood && wl >= nhood, BGAN_E_BADARG, "bgan_swd_feed_f32: level %d (%d x %d) smaller than the neighbourhood", l, hl, wl);
+        if (fused_gather) {
+            lv.level[l] = level;
+            lv.px[l] = px;
+            lv.out[l] = desc_out[l];
+            lv.sums[l] = sums[l];
+            lv.h[l] = hl;
+            lv.w[l] = wl;
+        } else {
+            const int rc = bgan_swd_extract_f32(level, n, c, hl, wl, px, py, nhoods_per_image, nhood, desc_out[l], sums[l], stream);  // :13-23
+            if (rc) return rc;
+        }
         hl /= 2;
         wl /= 2;
+    }
+    if (fused_gather) {  // :13-23 for every level
+        const int64_t ctas = std::min<int64_t>(ceil_div64(count, 8), 2 * static_cast<int64_t>(device_sm_count()));
+        extract_levels_kernel<4, 5><<<dim3(static_cast<unsigned>(ctas), levels), 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, c, nhoods_per_image, nhood, count);
+        BGAN_LAUNCH_OK();
     }
     return 0;
 }

@@ -176,18 +176,20 @@ def test_large_image_wide_halo(std, monkeypatch):
     assert ops.last_blur_path() in (1, 2, 3)
 
 
-@pytest.mark.parametrize("shape,std,no_sweep", [((40, 1, 1024, 256), 20.0, 0), ((40, 1, 256, 1024), 7.0, 0), ((24, 1, 512, 512), 12.0, 1),
-                                                 ((5, 1, 1024, 1024), 64.0, 0)])
-def test_axis_tensor_core_path_many_work_units_per_cta(shape, std, no_sweep, monkeypatch):
-    """Persistent CTAs that take several strips (sweep kernel, radius <= 128: 320 strips on 107 CTAs in the first pass of the
-    first case) or several tiles (tile kernel: radius > 128, or the sweep switched off) in a row: the hand-over of row scales,
-    accumulator slots and operand buffers from one work unit to the next.  Every plane is checked, the planes have different
-    magnitudes, and the TF rule at std 64 has radius 192 (nb = 2)."""
+@pytest.mark.parametrize("shape,std,unit_tiles", [((40, 1, 1024, 256), 20.0, 0), ((40, 1, 256, 1024), 7.0, 0), ((24, 1, 512, 512), 12.0, 1),
+                                                   ((24, 1, 512, 768), 30.0, 2), ((5, 1, 1024, 1024), 64.0, 0), ((3, 1, 640, 1024), 50.0, 1),
+                                                   ((4, 1, 896, 640), 75.0, 0)])
+def test_axis_tensor_core_path_many_work_units_per_cta(shape, std, unit_tiles, monkeypatch):
+    """Persistent CTAs that take several work units in a row -- whole strips (radius <= 128: 320 strips on 107 CTAs in the first
+    pass of the first case), pairs of tiles (radius > 128; 7 and 5 tiles per strip give a last unit of one tile) or, with the
+    unit size forced, single tiles and pairs at radius <= 128: the hand-over of row scales, accumulator slots, operand sets
+    and output boxes from one unit to the next.  Every plane is checked, the planes have different magnitudes; the TF rule at
+    std 50 / 64 / 75 has radius 150 / 192 / 225 (nb = 2)."""
     from blurred_gan_b200 import ops
     from blurred_gan_b200.gaussian_blur import blur_images
 
-    if no_sweep:
-        monkeypatch.setenv("BGAN_BLUR_AXIS_NO_SWEEP", "1")
+    if unit_tiles:
+        monkeypatch.setenv("BGAN_BLUR_AXIS_UNIT_TILES", str(unit_tiles))
     x = uniform_pm1(77, shape)
     x *= (10.0 ** np.random.RandomState(3).uniform(-4, 2, size=(shape[0], 1, 1, 1))).astype(np.float32)
     want = bo.blur_images_tf_ref(np.ascontiguousarray(x.transpose(0, 2, 3, 1)), std).transpose(0, 3, 1, 2)
