@@ -29,10 +29,14 @@ constexpr int kRadix = 256;
 __device__ __forceinline__ uint32_t float_to_ordered(uint32_t b) { return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
 __device__ __forceinline__ uint32_t ordered_to_float(uint32_t u) { return u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu); }
 
-template <bool FIRST>
-__device__ __forceinline__ uint32_t load_key(const uint32_t* __restrict__ p) {
-    const uint32_t v = __ldg(p);
-    return FIRST ? float_to_ordered(v) : v;
+// A single statement that "uses" all 16 loaded keys: nothing that consumes one of them can be scheduled before ALL the
+// loads have been issued.  Without it the first pass's float -> ordered-uint transforms were interleaved with the loads
+// (SASS: 16 LDG spread over 110 instructions), each transform waiting for its load, a handful of loads in flight per warp:
+// the first histogram pass ran at 2.8 TB/s (192 us) where the later ones, which have no transform, reach 5.5 TB/s (97 us).
+__device__ __forceinline__ void pin_loads(uint32_t (&k)[kItems]) {
+    static_assert(kItems == 16, "pin_loads lists 16 registers");
+    asm volatile("" : "+r"(k[0]), "+r"(k[1]), "+r"(k[2]), "+r"(k[3]), "+r"(k[4]), "+r"(k[5]), "+r"(k[6]), "+r"(k[7]), "+r"(k[8]), "+r"(k[9]),
+                      "+r"(k[10]), "+r"(k[11]), "+r"(k[12]), "+r"(k[13]), "+r"(k[14]), "+r"(k[15]));
 }
 
 // counts[(seg * tiles + tile) * 256 + digit]: one coalesced 1 KB row per tile, for the histogram's write and the
@@ -74,40 +78,33 @@ __device__ __forceinline__ uint32_t same_digit_lanes(uint32_t d) {
     }
 }
 
-template <bool FIRST, bool MATCH>
+// One shared-memory atomic per key into the warp's own histogram.  (Round 1 aggregated the top byte -- sign and exponent, a
+// handful of values per 32 keys -- with match_any first; measured in round 2, the sixteen match_any per thread cost more
+// than the conflicts they avoid: 209 us against ~100 us per pass of 134 M keys, 60.9 -> 64.3 Gkeys/s for the whole sort.)
+template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t rows, int tiles, int shift,
                                                                   uint32_t* __restrict__ counts) {
     __shared__ uint32_t s_cnt[kSortWarps][kRadix];
     const int tile = blockIdx.x, seg = blockIdx.y;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < kSortWarps * kRadix / 4; i += kSortThreads) reinterpret_cast<uint4*>(&s_cnt[0][0])[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     const uint32_t* src = keys + static_cast<size_t>(seg) * rows + static_cast<size_t>(tile) * kTile;
     const int valid = (rows - static_cast<int64_t>(tile) * kTile < kTile) ? static_cast<int>(rows - static_cast<int64_t>(tile) * kTile) : kTile;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    // MATCH (top byte: a handful of distinct digits per 32-key row): one shared-memory atomic per distinct digit;
-    // otherwise (digits close to uniform: conflicts are rare) one atomic per key
     // all 16 loads of the thread first: issued between the shared-memory atomics they were serialised (18 registers, one
     // load in flight per warp, "long scoreboard" 41 - 51 per issue in ncu: 2.3 TB/s); up front they are 16 x 128 B per warp
     uint32_t key[kItems];
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
         const int local = i * kSortThreads + tid;
-        key[i] = local < valid ? load_key<FIRST>(src + local) : 0u;
+        key[i] = local < valid ? __ldg(src + local) : 0u;
     }
+    pin_loads(key);
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
-        const int local = i * kSortThreads + tid;
-        const bool ok = local < valid;
-        const uint32_t d = ok ? (key[i] >> shift) & 0xff : 256u;
-        if constexpr (MATCH) {
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            if (ok && (peers & lt_mask) == 0) atomicAdd(&s_cnt[warp][d], static_cast<uint32_t>(__popc(peers)));
-        } else {
-            if (ok) atomicAdd(&s_cnt[warp][d], 1u);
-        }
+        const uint32_t k = FIRST ? float_to_ordered(key[i]) : key[i];
+        if (i * kSortThreads + tid < valid) atomicAdd(&s_cnt[warp][(k >> shift) & 0xff], 1u);
     }
-    (void)lt_mask;
     __syncthreads();
     uint32_t total = 0;
 #pragma unroll
@@ -223,7 +220,12 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem& sm, const uint32_t* __
     for (int i = 0; i < kItems; ++i) {
         const int local = warp_base + i * 32 + lane;
         const bool ok = FULL || local < valid;
-        key[i] = ok ? load_key<FIRST>(src + local) : 0xffffffffu;
+        key[i] = ok ? __ldg(src + local) : (FIRST ? 0x7fffffffu : 0xffffffffu);  // (padding: the largest key either way)
+    }
+    pin_loads(key);
+    if constexpr (FIRST) {
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) key[i] = float_to_ordered(key[i]);
     }
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
@@ -381,19 +383,19 @@ static int sort_passes(float* keys_device, int64_t rows, int segments, void* ws,
     const DiffArgs none{nullptr, nullptr, 0, 1};
 
     // pass 0: a -> b (float -> ordered uint on load)
-    radix_hist_kernel<true, false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 0, counts);
+    radix_hist_kernel<true><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 0, counts);
     scan();
     radix_scatter_kernel<true, false, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 0, offsets, none);
     // pass 1: b -> a
-    radix_hist_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 8, counts);
+    radix_hist_kernel<false><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 8, counts);
     scan();
     radix_scatter_kernel<false, false, false, false><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 8, offsets, none);
     // pass 2: a -> b
-    radix_hist_kernel<false, false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 16, counts);
+    radix_hist_kernel<false><<<grid, kSortThreads, 0, stream>>>(a, rows, tiles, 16, counts);
     scan();
     radix_scatter_kernel<false, false, false, false><<<grid, kSortThreads, 0, stream>>>(a, b, rows, tiles, 16, offsets, none);
     // pass 3: b -> a (ordered uint -> float on store), or b -> sum |ref - key|
-    radix_hist_kernel<false, true><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 24, counts);
+    radix_hist_kernel<false><<<grid, kSortThreads, 0, stream>>>(b, rows, tiles, 24, counts);
     scan();
     if (da.ref != nullptr)
         radix_scatter_kernel<false, true, true, true><<<grid, kSortThreads, 0, stream>>>(b, a, rows, tiles, 24, offsets, da);

@@ -322,6 +322,38 @@ def test_full_size_properties(std):
     assert_close(bx.view(768, 1, 128, 128)[idx], want, "full-size spot check")
 
 
+@pytest.mark.parametrize("std", [8.0, 64.0])
+def test_full_size_properties_large_images(std):
+    """BASELINE configs[3] at full size (32 x 3 x 1024 x 1024, TF rule): size-independent properties of the two-pass
+    tensor-core kernel (whole-strip units at std 8, pairs of tiles at std 64), and the NHWC route against the NCHW one."""
+    from blurred_gan_b200 import ops
+    from blurred_gan_b200.gaussian_blur import blur_images
+
+    torch.manual_seed(0)
+    x = torch.rand(32, 3, 1024, 1024, device="cuda") * 2 - 1
+    y = torch.rand(32, 3, 1024, 1024, device="cuda") * 2 - 1
+    bx, by = blur_images(x, std), blur_images(y, std)
+    assert ops.last_blur_path() == 6
+    # self-adjoint: <Bx, y> == <x, By>
+    lhs, rhs = (bx.double() * y.double()).sum().item(), (x.double() * by.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+    # linear
+    z = blur_images(2.0 * x - 0.5 * y, std)
+    assert (z - (2.0 * bx - 0.5 * by)).abs().max().item() <= 1e-5 * max(bx.abs().max().item(), 1e-3) * 3
+    del z, by, y
+    # every plane is treated alike: plane 77 alone (one strip unit per CTA) == plane 77 of the batch (six units per CTA)
+    single = blur_images(x.view(96, 1, 1024, 1024)[77:78].reshape(1, 1, 1024, 1024).expand(1, 2, 1024, 1024).contiguous(), std)
+    assert torch.equal(single[0, 0], bx.view(96, 1024, 1024)[77]) and torch.equal(single[0, 1], single[0, 0])
+    # NHWC images of the same data go through the planar route (path 7): the same bits
+    xh = x[:4].permute(0, 2, 3, 1).contiguous()
+    yh = blur_images(xh, std)
+    assert ops.last_blur_path() == 7
+    assert torch.equal(yh.permute(0, 3, 1, 2), bx[:4])
+    # one plane against the oracle
+    xs = x[31:32, 2:3].permute(0, 2, 3, 1).cpu().numpy()
+    assert_close(bx[31, 2], bo.blur_images_tf_ref(np.ascontiguousarray(xs), std)[0, :, :, 0], "full-size spot check, std=%g" % std)
+
+
 def test_ones_image_border_profile_and_errors():
     from blurred_gan_b200 import ops
     from blurred_gan_b200.pytorch.gaussianblur import GaussianBlur
