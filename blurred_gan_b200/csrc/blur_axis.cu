@@ -89,7 +89,6 @@ struct AxisArgs {
     int unit_tiles;           // output tiles per work unit (nb = 1: tiles_j, the whole strip; nb = 2: 2)
     int units_per_strip;      // ceil(tiles_j / unit_tiles)
     int n_units;              // planes * tiles_i * units_per_strip
-    int reverse;              // walk the units last plane first (the pass then starts on what the previous kernel left in L2)
     int nb;                   // ceil(radius / 128)
     int rule;
     float std_eff;
@@ -232,7 +231,6 @@ struct Unit {
 };
 __device__ __forceinline__ Unit unit_of(const AxisArgs& a, int idx) {
     Unit u;
-    if (a.reverse) idx = a.n_units - 1 - idx;
     const int g = idx % a.units_per_strip, strip = idx / a.units_per_strip;
     u.plane = strip / a.tiles_i;
     u.ib = strip - u.plane * a.tiles_i;
@@ -600,7 +598,7 @@ int launch_axis_mode(const AxisArgs& a, const float* in, float* out, int planes,
 
 // one pass: in [planes][I][K] -> out [planes][K][I]
 int launch_axis(const float* in, float* out, const float* rowmax_in, float* rowmax_out, int planes, int I, int K, int rule, float std_eff,
-                int radius, const float* taps_dev, bool reverse, cudaStream_t stream) {
+                int radius, const float* taps_dev, cudaStream_t stream) {
     thread_local bool bound = false;
     if (!bound) {
         cudaFree(nullptr);
@@ -631,7 +629,6 @@ int launch_axis(const float* in, float* out, const float* rowmax_in, float* rowm
     a.units_per_strip = ceil_div(a.tiles_j, a.unit_tiles);
     const int64_t units = static_cast<int64_t>(planes) * a.tiles_i * a.units_per_strip;
     a.n_units = static_cast<int>(units);
-    a.reverse = reverse ? 1 : 0;
     if (a.nb == 1) return launch_axis_mode<false>(a, in, out, planes, I, K, units, stream);
     return launch_axis_mode<true>(a, in, out, planes, I, K, units, stream);
 }
@@ -672,11 +669,9 @@ int blur_axis_launch(const float* x, float* y, int planes, int H, int W, int rul
     rowmax_kernel<<<static_cast<unsigned>(ceil_div64(rows * 32, 256)), 256, 0, stream>>>(x, rows, W, rm_x);
     BGAN_LAUNCH_OK();
     BGAN_CUDA_OK(cudaMemsetAsync(rm_z, 0, static_cast<size_t>(planes) * W * sizeof(float), stream));
-    // The row-maximum pre-pass reads x first plane first, so its last ~100 MB are what is left in the 126 MB L2: pass 1 walks
-    // the planes backwards and starts on them, pass 2 forwards again and starts on the intermediate planes pass 1 wrote last.
-    int rc = launch_axis(x, mid, rm_x, rm_z, planes, H, W, rule, std_eff, radius, taps_dev, true, stream);  // blur along W: X[h][w] -> Z^T[w'][h]
+    int rc = launch_axis(x, mid, rm_x, rm_z, planes, H, W, rule, std_eff, radius, taps_dev, stream);  // blur along W: X[h][w] -> Z^T[w'][h]
     if (rc) return rc;
-    return launch_axis(mid, y, rm_z, nullptr, planes, W, H, rule, std_eff, radius, taps_dev, false, stream);  // blur along H: Z^T[w'][h] -> Y[h'][w']
+    return launch_axis(mid, y, rm_z, nullptr, planes, W, H, rule, std_eff, radius, taps_dev, stream);  // blur along H: Z^T[w'][h] -> Y[h'][w']
 }
 
 }  // namespace bgan
