@@ -50,6 +50,7 @@ def parse_args():
     p.add_argument("--no-swd", action="store_true", help="skip the secondary SWD timing")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-large", action="store_true", help="skip the 1024 x 1024 context rows (BASELINE configs[3])")
+    p.add_argument("--no-train-step", action="store_true", help="skip the WGAN-GP train-step context row (BASELINE configs[2])")
     p.add_argument("--swd-images", type=int, default=16384, help="images per set for the secondary SWD timing (BASELINE configs[4]: 16384)")
     p.add_argument("--swd-cpu-images", type=int, default=512, help="images per set for the SWD CPU baseline (bounded sample)")
     p.add_argument("--stds", type=str, default="", help="comma-separated override of the std sweep (profiling runs)")
@@ -503,10 +504,11 @@ def run_native(args, stds):
         e2e_steps = max(2, min(args.steps, 5))
         for _ in range(2):
             e2e_step()
-        # three windows of e2e_steps steps, the median window is reported: the pipeline is driven by the host (copies, module
-        # calls, the autograd thread), and a single hiccup of a shared host otherwise decides the number
+        # seven windows of e2e_steps steps, the median window is reported: the pipeline is driven by the host (copies, module
+        # calls, the autograd thread), and a hiccup of a shared host otherwise decides the number (one round-2 run on a busy
+        # box had two of three windows 25 % slower than the third)
         windows, windows_local = [], []
-        for _ in range(3):
+        for _ in range(7):
             barrier()
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
@@ -520,7 +522,7 @@ def run_native(args, stds):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             windows.append(dt)
-        dt = sorted(windows)[1]
+        dt = sorted(windows)[len(windows) // 2]
         # The ceiling of this pipeline: the same pinned buffers copied host -> device and device -> host on the two copy
         # streams, both directions at once, no kernels -- measured at the same world size in the same run (all ranks copy
         # at the same time, like in the timed windows above).
@@ -544,7 +546,7 @@ def run_native(args, stds):
             torch.cuda.synchronize(dev)
             cwin.append(time.perf_counter() - t0)
         cdt_local = sorted(cwin)[1]
-        dt_local = sorted(windows_local)[1]
+        dt_local = sorted(windows_local)[len(windows_local) // 2]
         per_dir = 2 * plane_bytes * len(stds) * e2e_steps  # bytes per direction per rank per window
         stats = torch.tensor([dt_local, cdt_local], device=dev, dtype=torch.float64)
         if world > 1:
@@ -579,6 +581,21 @@ def run_native(args, stds):
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(stds)
+    if not args.no_train_step:  # context: BASELINE configs[2], every rank takes part (gradient all-reduce)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import train_step
+
+            ts = train_step.run(global_batch=256, steps=4, warmup=2, std=5.0, fused_critic=False)
+            tf = train_step.run(global_batch=256, steps=4, warmup=2, std=5.0, fused_critic=True)
+            line["train_step_cfg3"] = {
+                "what": ts["config"]["workload"] + "; the nets are cuDNN fp32 (library code, outside the path); the blur's share is what the path adds",
+                "ms_per_step": round(ts["ms_per_step"], 3), "images_per_s": round(ts["value"], 1),
+                "ms_per_step_without_blur": round(ts["ms_per_step_without_blur"], 3), "blur_share_of_step": round(ts["blur_share_of_step"], 4),
+                "fused_critic_ms_per_step": round(tf["ms_per_step"], 3), "blur_applications_per_step": [7, 6]}
+            torch.cuda.empty_cache()
+        except Exception as exc:  # context row: never lose the headline line
+            line["train_step_cfg3"] = {"error": repr(exc)}
     if not args.no_swd:  # every rank takes part (sharded feed, NCCL exchange)
         try:
             swd = swd_timing(args.swd_images, dev, rank, world, hbm_peak)

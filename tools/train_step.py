@@ -63,6 +63,38 @@ def timed_steps(gan, reals, ctl, steps, warmup, world):
     return ms
 
 
+def run(global_batch=256, steps=20, warmup=5, std=5.0, fused_critic=False):
+    """The measurement as a function (bench.py calls it for its `train_step_cfg3` context row).  Uses the current CUDA device and
+    the default process group when one is initialised; returns the result dict on every rank."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    per_rank = global_batch // world
+    out = {}
+    metrics = None
+    for kind in ("blur", "identity"):
+        torch.manual_seed(0)  # identical initial weights on every rank
+        hp = BlurredWGANGP.HyperParameters(batch_size=per_rank, global_batch_size=global_batch, initial_blur_std=std)
+        blur = GaussianBlur2D(std) if kind == "blur" else _Identity()
+        gan = BlurredWGANGP(nets.CelebaGenerator(), nets.CelebaDiscriminator(), hp, blur=blur, fused_critic=fused_critic and kind == "blur",
+                            grad_sync=allreduce_gradients if world > 1 else None).cuda()
+        ctl = callbacks.BlurDecayController(total_n_training_examples=202599 * 10, max_value=std)
+        ctl.set_model(gan)
+        torch.manual_seed(1000 + rank)
+        reals = torch.rand(per_rank, 3, 128, 128, device="cuda") * 2 - 1
+        out[kind] = timed_steps(gan, reals, ctl, steps, warmup, world)
+        if kind == "blur":
+            metrics = gan.metric_results()
+        del gan, reals
+    ms, ms_id = out["blur"], out["identity"]
+    return {
+        "metric": "blurred WGAN-GP train step images/s at 128x128x3", "value": global_batch / (ms * 1e-3), "unit": "images/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3: BlurredWGANGP.train_on_batch, CelebA-128 DCGAN nets, global batch %d sharded over %d GPU(s), std %.2f" % (
+            global_batch, world, std), "blur_applications_per_step": 6 if fused_critic else 7, "fused_critic": bool(fused_critic)},
+        "ms_per_step_without_blur": ms_id, "blur_share_of_step": max(ms - ms_id, 0.0) / ms,
+        "last_metrics": metrics}
+
+
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--global-batch", type=int, default=256)
@@ -78,30 +110,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    per_rank = a.global_batch // world
-    out = {}
-    for kind in ("blur", "identity"):
-        torch.manual_seed(0)  # identical initial weights on every rank
-        hp = BlurredWGANGP.HyperParameters(batch_size=per_rank, global_batch_size=a.global_batch, initial_blur_std=a.std)
-        blur = GaussianBlur2D(a.std) if kind == "blur" else _Identity()
-        gan = BlurredWGANGP(nets.CelebaGenerator(), nets.CelebaDiscriminator(), hp, blur=blur, fused_critic=a.fused_critic and kind == "blur",
-                            grad_sync=allreduce_gradients if world > 1 else None).cuda()
-        ctl = callbacks.BlurDecayController(total_n_training_examples=202599 * 10, max_value=a.std)
-        ctl.set_model(gan)
-        torch.manual_seed(1000 + rank)
-        reals = torch.rand(per_rank, 3, 128, 128, device="cuda") * 2 - 1
-        out[kind] = timed_steps(gan, reals, ctl, a.steps, a.warmup, world)
-        if kind == "blur":
-            metrics = gan.metric_results()
+    res = run(a.global_batch, a.steps, a.warmup, a.std, a.fused_critic)
     if rank == 0:
-        ms, ms_id = out["blur"], out["identity"]
-        print(json.dumps({
-            "metric": "blurred WGAN-GP train step images/s at 128x128x3", "value": a.global_batch / (ms * 1e-3), "unit": "images/s",
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "scaling": "strong", "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3: BlurredWGANGP.train_on_batch, CelebA-128 DCGAN nets, global batch %d sharded over %d GPU(s), std %.2f" % (
-                a.global_batch, world, a.std), "blur_applications_per_step": 6 if a.fused_critic else 7, "fused_critic": bool(a.fused_critic)},
-            "ms_per_step_without_blur": ms_id, "blur_share_of_step": max(ms - ms_id, 0.0) / ms,
-            "last_metrics": metrics}), flush=True)
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
