@@ -11,7 +11,8 @@ lib = _lib.load()
 n, c, h, w = 256, 3, 128, 128
 std = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
 variant, early, pipe = 0, False, True
-xs = [torch.rand(n, c, h, w, device="cuda") * 2 - 1 for _ in range(4)]
+nhwc = len(sys.argv) > 2 and sys.argv[2] == "nhwc"
+xs = [torch.rand(*((n, h, w, c) if nhwc else (n, c, h, w)), device="cuda") * 2 - 1 for _ in range(4)]
 ys = [torch.empty_like(x) for x in xs]
 trace = torch.zeros(512, dtype=torch.int64, device="cuda")
 k, r, se = _lib.blur_plan(0, std, h, w)
@@ -19,7 +20,7 @@ sp = torch.cuda.current_stream().cuda_stream
 for rep in range(4):
     if rep == 3:
         os.environ["BGAN_TC_TRACE_PTR"] = str(trace.data_ptr())
-    _lib.check(lib.bgan_blur2d_f32(xs[rep].data_ptr(), ys[rep].data_ptr(), n, c, h, w, 0, 0, se, r, None, None, 0, sp), "blur")
+    _lib.check(lib.bgan_blur2d_f32(xs[rep].data_ptr(), ys[rep].data_ptr(), n, c, h, w, 1 if nhwc else 0, 0, se, r, None, None, 0, sp), "blur")
 torch.cuda.synchronize()
 t = trace.cpu().tolist()
 cnt = t[0]
