@@ -16,7 +16,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libbgan_b200.so")
-SOURCES = ["capi.cu", "blur.cu", "blur_tc.cu", "blur_direct.cu", "blur_axis.cu", "swd.cu", "project_tc.cu", "sort.cu", "hostrng.cu"]
+SOURCES = ["capi.cu", "blur.cu", "blur_tc.cu", "blur_direct.cu", "blur_axis.cu", "swd.cu", "project_tc.cu", "sort.cu", "sort_sample.cu", "hostrng.cu"]
 # host-only sources compiled by g++ (name -> extra flags); selected at run time by a CPU feature check in hostrng.cu
 CPP_SOURCES = {"hostrng_avx2.cpp": ["-mavx2"], "hostrng_avx512.cpp": ["-mavx512f"]}
 NVCC_FLAGS = [

@@ -14,8 +14,9 @@
 // Tile = 256 threads x 16 keys.  The float<->uint transform is fused into the first load and the
 // last store, so the sort runs in place from the caller's point of view (ping-pong through ws).
 #include <algorithm>
+#include <cstdlib>
 
-#include "common.cuh"
+#include "sort.cuh"
 
 namespace bgan {
 namespace {
@@ -25,9 +26,6 @@ constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItems = 16;
 constexpr int kTile = kSortThreads * kItems;  // 4096 keys
 constexpr int kRadix = 256;
-
-__device__ __forceinline__ uint32_t float_to_ordered(uint32_t b) { return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
-__device__ __forceinline__ uint32_t ordered_to_float(uint32_t u) { return u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu); }
 
 // A single statement that "uses" all 16 loaded keys: nothing that consumes one of them can be scheduled before ALL the
 // loads have been issued.  Without it the first pass's float -> ordered-uint transforms were interleaved with the loads
@@ -179,16 +177,6 @@ struct ScatterSmem {
     uint32_t keys[kTile];
     uint32_t scan[kSortWarps];
     double diff[kSortWarps];
-};
-
-// The |a - b| partial sums of the fused last pass go to kDiffSlots accumulators per sum (tile % kDiffSlots), added up by a
-// one-CTA kernel afterwards: tiles x segments fp64 atomics on a handful of addresses would serialise in L2.
-constexpr int kDiffSlots = 64;
-struct DiffArgs {
-    const float* ref;     // sorted reference segments (same layout as the keys), or nullptr
-    double* partial;      // [sums][kDiffSlots]
-    int seg_offset;       // sum index of segment s = (s + seg_offset) / segs_per_sum
-    int segs_per_sum;
 };
 
 // DIFF (only with LAST): the keys are not written; every key meets the element of `ref` that sits at its final position
@@ -354,13 +342,26 @@ static int scan_chunks(int64_t tiles) {
     return static_cast<int>(std::min<int64_t>(kMaxScanChunks, std::max<int64_t>(1, ceil_div64(tiles, kScanChunkTiles))));
 }
 
-extern "C" size_t bgan_swd_sort_workspace_bytes(int64_t rows, int segments) {
-    if (rows <= 0 || segments <= 0) return 0;
+static size_t lsd_workspace_bytes(int64_t rows, int segments) {
     const int64_t tiles = ceil_div64(rows, kTile);
     const size_t keys = static_cast<size_t>(rows) * segments * sizeof(uint32_t);
     const size_t counts = static_cast<size_t>(segments) * kRadix * tiles * sizeof(uint32_t);
     const size_t part = static_cast<size_t>(segments) * kRadix * scan_chunks(tiles) * sizeof(uint32_t);
     return ((keys + 255) & ~size_t(255)) + 2 * counts + part;  // keys | counts | offsets | chunk partials
+}
+
+// Which sort runs: the splitter / shared-memory-bucket sort (sort_sample.cu) for segments it holds, else the radix passes below.
+// BGAN_SORT_ALGO=lsd forces the radix sort (A/B measurements).
+static bool use_sample_sort(int64_t rows) {
+    const char* algo = getenv("BGAN_SORT_ALGO");
+    if (algo && algo[0] == 'l') return false;
+    return sample_sort_applicable(rows);
+}
+
+extern "C" size_t bgan_swd_sort_workspace_bytes(int64_t rows, int segments) {
+    if (rows <= 0 || segments <= 0) return 0;
+    // the radix sort is the fall-back of the sample sort and runs in the same workspace
+    return std::max(lsd_workspace_bytes(rows, segments), sample_sort_applicable(rows) ? sample_sort_workspace_bytes(rows, segments) : size_t(0));
 }
 
 // The four passes over `segments` runs of `rows` keys at keys_device; with `da.ref` the last pass does not write the keys
@@ -405,13 +406,35 @@ static int sort_passes(float* keys_device, int64_t rows, int segments, void* ws,
     return 0;
 }
 
+// One array of segments: the sample sort when it applies, with the radix passes as its fall-back.  The sample sort reports a
+// bucket that does not fit shared memory through a device flag and then has written nothing, so the fall-back starts from
+// the untouched keys; reading the flag costs one 4-byte device -> host copy (and a stream synchronisation) per call for
+// segments of more than 8192 keys.  A stream that is being captured cannot be synchronised: it takes the radix passes.
+static int sort_one(float* keys_device, int64_t rows, int segments, void* ws, cudaStream_t stream, const DiffArgs& da) {
+    if (use_sample_sort(rows)) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        BGAN_CUDA_OK(cudaStreamIsCapturing(stream, &cap));
+        const uint32_t* flag_device = nullptr;
+        if (cap == cudaStreamCaptureStatusNone || rows <= 8192) {
+            const int rc = sample_sort_launch(keys_device, rows, segments, ws, stream, da, &flag_device);
+            if (rc) return rc;
+            if (flag_device == nullptr) return 0;
+            uint32_t flag = 0;
+            BGAN_CUDA_OK(cudaMemcpyAsync(&flag, flag_device, sizeof(flag), cudaMemcpyDeviceToHost, stream));
+            BGAN_CUDA_OK(cudaStreamSynchronize(stream));
+            if (flag == 0) return 0;
+        }
+    }
+    return sort_passes(keys_device, rows, segments, ws, stream, da);
+}
+
 extern "C" int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws, size_t ws_bytes, void* stream_) {
     BGAN_REQUIRE(keys_device && rows > 0 && segments > 0, BGAN_E_BADARG, "bgan_swd_sort_f32: bad arguments");
     BGAN_REQUIRE(rows < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_swd_sort_f32: at most 2^31-1 rows per segment");
     BGAN_REQUIRE(segments <= 65535, BGAN_E_BADARG, "bgan_swd_sort_f32: at most 65535 segments per call");
     BGAN_REQUIRE(ws && ws_bytes >= bgan_swd_sort_workspace_bytes(rows, segments), BGAN_E_WORKSPACE,
                  "bgan_swd_sort_f32: workspace of %zu bytes required, got %zu", bgan_swd_sort_workspace_bytes(rows, segments), ws_bytes);
-    return sort_passes(keys_device, rows, segments, ws, static_cast<cudaStream_t>(stream_), DiffArgs{nullptr, nullptr, 0, 1});
+    return sort_one(keys_device, rows, segments, ws, static_cast<cudaStream_t>(stream_), DiffArgs{nullptr, nullptr, 0, 1});
 }
 
 static size_t diff_partial_bytes(int n_sums) { return static_cast<size_t>(n_sums) * kDiffSlots * sizeof(double); }
@@ -433,10 +456,10 @@ extern "C" int bgan_swd_sort_diff_f32(float* a_device, float* b_device, int64_t 
                  ws_bytes);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     double* partial = reinterpret_cast<double*>(static_cast<char*>(ws) + ((bgan_swd_sort_workspace_bytes(rows, segments) + 255) & ~size_t(255)));
-    int rc = sort_passes(a_device, rows, segments, ws, stream, DiffArgs{nullptr, nullptr, 0, 1});  // A: sorted in place
+    int rc = sort_one(a_device, rows, segments, ws, stream, DiffArgs{nullptr, nullptr, 0, 1});  // A: sorted in place
     if (rc) return rc;
     BGAN_CUDA_OK(cudaMemsetAsync(partial, 0, diff_partial_bytes(n_sums), stream));
-    rc = sort_passes(b_device, rows, segments, ws, stream, DiffArgs{a_device, partial, seg_offset, segs_per_sum});  // B: three passes, then the diff
+    rc = sort_one(b_device, rows, segments, ws, stream, DiffArgs{a_device, partial, seg_offset, segs_per_sum});  // B: never written back
     if (rc) return rc;
     diff_finish_kernel<<<ceil_div(n_sums, 4), 128, 0, stream>>>(partial, n_sums, sums_device);
     BGAN_LAUNCH_OK();

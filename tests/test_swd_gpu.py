@@ -122,10 +122,18 @@ def test_projection_long_descriptors_use_the_fma_kernel():
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
 
 
-@pytest.mark.parametrize("segments,rows", [(1, 1), (3, 5), (2, 4096), (5, 4097), (130, 1000), (4, 100000), (1, 1 << 20)])
-def test_segmented_sort_is_exact(segments, rows):
+@pytest.mark.parametrize("algo", ["default", "lsd", "fallback"])
+@pytest.mark.parametrize("segments,rows", [(1, 1), (3, 5), (2, 4096), (5, 4097), (130, 1000), (3, 8192), (3, 8193), (4, 100000), (4, 100001),
+                                           (1, 1 << 20), (2, 1 << 21), (1, (1 << 21) + 1)])
+def test_segmented_sort_is_exact(segments, rows, algo, monkeypatch):
+    """Three routes: the splitter / shared-memory-bucket sort (segments of up to 2^21 keys), the radix passes alone, and the
+    radix passes entered through the sample sort's overflow flag."""
     from blurred_gan_b200 import ops
 
+    if algo == "lsd":
+        monkeypatch.setenv("BGAN_SORT_ALGO", "lsd")
+    if algo == "fallback":
+        monkeypatch.setenv("BGAN_SORT_FORCE_FALLBACK", "1")
     rs = np.random.RandomState(segments * 7919 + rows)
     keys = (rs.randn(segments, rows) * 10.0 ** rs.randint(-3, 4, size=(segments, 1))).astype(np.float32)
     if rows >= 5:
@@ -137,6 +145,53 @@ def test_segmented_sort_is_exact(segments, rows):
     got = ops.swd_sort_(_dev(keys)).cpu().numpy()
     want = np.sort(keys, axis=1)
     np.testing.assert_array_equal(got, want)  # (-0.0 == 0.0 compares equal; order among them is irrelevant)
+
+
+def _sort_case(name, rs, segments, rows):
+    if name == "all_equal":
+        return np.full((segments, rows), 0.25, np.float32)
+    if name == "ten_values":  # every value far too frequent to sort: equality buckets
+        return rs.randint(0, 10, size=(segments, rows)).astype(np.float32) - 4.5
+    if name == "ascending":
+        return np.sort(rs.randn(segments, rows).astype(np.float32), axis=1)
+    if name == "descending":
+        return -np.sort(rs.randn(segments, rows).astype(np.float32), axis=1)
+    if name == "half_zero":  # one heavy value in a continuous distribution
+        k = rs.randn(segments, rows).astype(np.float32)
+        k[rs.rand(segments, rows) < 0.5] = 0.0
+        return k
+    if name == "outliers":  # a tight cluster and a few values 36 orders of magnitude away
+        k = (rs.rand(segments, rows) * 1e-6).astype(np.float32)
+        k[:, ::1000] = 1e30
+        k[:, 1::1000] = -1e30
+        return k
+    if name == "clusters":  # near-duplicates at many scales: sub-buckets overload, the bitonic route sorts them
+        k = (10.0 ** rs.randint(-30, 30, size=(segments, rows))).astype(np.float32)
+        return k * (1 + 1e-6 * rs.rand(segments, rows)).astype(np.float32) * rs.choice([-1.0, 1.0], size=(segments, rows)).astype(np.float32)
+    if name == "lognormal":
+        return np.exp(rs.randn(segments, rows) * 8).astype(np.float32)
+    if name == "nonfinite":
+        k = rs.randn(segments, rows).astype(np.float32)
+        k[:, ::7] = np.inf
+        k[:, 3::11] = -np.inf
+        return k
+    if name == "denormals":
+        return (rs.randn(segments, rows) * 1e-41).astype(np.float32)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("rows", [5000, 70001, 300000])
+@pytest.mark.parametrize("name", ["all_equal", "ten_values", "ascending", "descending", "half_zero", "outliers", "clusters", "lognormal",
+                                  "nonfinite", "denormals"])
+def test_segmented_sort_is_exact_whatever_the_distribution(name, rows):
+    """The bucket boundaries come from a sample of the keys and the sub-buckets from a linear map of the value: neither may
+    cost correctness when the keys are nothing like a smooth density."""
+    from blurred_gan_b200 import ops
+
+    rs = np.random.RandomState(rows + len(name))
+    keys = _sort_case(name, rs, 3, rows)
+    got = ops.swd_sort_(_dev(keys)).cpu().numpy()
+    np.testing.assert_array_equal(got, np.sort(keys, axis=1))
 
 
 def test_absdiff_sum():
