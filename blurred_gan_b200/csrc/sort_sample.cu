@@ -42,13 +42,14 @@ constexpr int kSsMaxCells = kSsMaxBuckets * kSsCellsPerBucket;
 constexpr int kSsCap = 8192;           // keys a local-sort CTA holds
 constexpr int kSsBlock = 16384;        // keys per (classify, scatter) block: one row of counts / bases
 constexpr int kSsClsBlocks = 4;        // blocks per classify CTA (one load of the lut)
-constexpr int kSsThreads = 256;        // classify / scatter
+constexpr int kSsThreads = 256;        // classify
+constexpr int kScThreads = 256;        // scatter (512: measured slower, 365 against 340 us)
 constexpr int64_t kSsMaxRows = int64_t(1) << 21;
 constexpr int kModelThreads = 1024;    // model / scan kernels
 constexpr int kLsThreads = 512;        // local sort
 constexpr int kLsWarps = kLsThreads / 32;
 constexpr int kLsItems = kSsCap / kLsThreads;  // 16 keys per thread
-constexpr int kLsMaxSub = 4096;
+constexpr int kLsMaxSub = 8192;         // sub-buckets of a run: the power of two >= its keys (0.5 .. 1 key per sub-bucket)
 constexpr int kLsBatchIds = 16;        // buckets per ticket
 
 struct SsPlan {
@@ -108,6 +109,10 @@ __device__ __forceinline__ int linear_cell(uint32_t float_bits, float lo, float 
     int c = min(cells - 1, max(0, __float2int_rz((x - lo) * scale)));
     if (x != x) c = (float_bits >> 31) ? 0 : cells - 1;
     return c;
+}
+// the same for keys known not to be NaN
+__device__ __forceinline__ int linear_cell_finite(uint32_t float_bits, float lo, float scale, int cells) {
+    return min(cells - 1, max(0, __float2int_rz((__uint_as_float(float_bits) - lo) * scale)));
 }
 
 // ---- bitonic network over n (a power of two) ordered keys in shared memory; ends with a barrier --------------------------
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(kModelThreads) ss_scan_kernel(const uint16_t* 
 // ---- scatter -------------------------------------------------------------------------------------------------------------------
 constexpr size_t kScatterSmem = kSsBlock * sizeof(uint32_t) + kSsBlock * sizeof(uint16_t) + 2 * kSsMaxBuckets * sizeof(uint32_t) + 64;
 
-__global__ void __launch_bounds__(kSsThreads, 2) ss_scatter_kernel(const uint32_t* __restrict__ keys, const uint16_t* __restrict__ ids,
+__global__ void __launch_bounds__(kScThreads, 2) ss_scatter_kernel(const uint32_t* __restrict__ keys, const uint16_t* __restrict__ ids,
                                                                    int64_t rows, int buckets, int blocks, const uint16_t* __restrict__ counts,
                                                                    const uint32_t* __restrict__ bases, uint32_t* __restrict__ out,
                                                                    const uint32_t* __restrict__ ctrl) {
@@ -321,8 +326,8 @@ __global__ void __launch_bounds__(kSsThreads, 2) ss_scatter_kernel(const uint32_
     const int blk = blockIdx.x, seg = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t row = (static_cast<size_t>(seg) * blocks + blk) * buckets;
     // local starts: exclusive scan of this block's counts; thread t owns `per` consecutive ids
-    constexpr int kMaxPer = kSsMaxBuckets / kSsThreads;
-    const int per = (buckets + kSsThreads - 1) / kSsThreads;  // 1 .. 4
+    constexpr int kMaxPer = kSsMaxBuckets / kScThreads;
+    const int per = (buckets + kScThreads - 1) / kScThreads;  // 1 .. 4
     uint32_t c[kMaxPer];
     uint32_t sum = 0;
 #pragma unroll
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(kSsThreads, 2) ss_scatter_kernel(const uint32_
     if ((at & 3) == 0) {
         const int vec = valid >> 2;
 #pragma unroll 4
-        for (int v = tid; v < vec; v += kSsThreads) {
+        for (int v = tid; v < vec; v += kScThreads) {
             const uint4 k = __ldg(reinterpret_cast<const uint4*>(src) + v);
             const uint2 i2 = __ldg(reinterpret_cast<const uint2*>(sid) + v);
             const uint32_t id0 = i2.x & 0xffff, id1 = i2.x >> 16, id2 = i2.y & 0xffff, id3 = i2.y >> 16;
@@ -373,26 +378,27 @@ __global__ void __launch_bounds__(kSsThreads, 2) ss_scatter_kernel(const uint32_
         }
         done = vec << 2;
     }
-    for (int i = done + tid; i < valid; i += kSsThreads) {
+    for (int i = done + tid; i < valid; i += kScThreads) {
         const uint32_t id = sid[i], p = atomicAdd(&s_cur[id], 1u);
         s_key[p] = __ldg(src + i), s_id[p] = static_cast<uint16_t>(id);
     }
     __syncthreads();
     uint32_t* dst = out + static_cast<size_t>(seg) * rows;
 #pragma unroll 4
-    for (int slot = tid; slot < valid; slot += kSsThreads) dst[s_delta[s_id[slot]] + slot] = s_key[slot];
+    for (int slot = tid; slot < valid; slot += kScThreads) dst[s_delta[s_id[slot]] + slot] = s_key[slot];
 }
 
 // ---- local sort ------------------------------------------------------------------------------------------------------------------
 struct LocalSmem {
-    uint32_t buf[kSsCap];
+    uint32_t buf[kSsCap + 4];  // (+4: the ranking step probes up to four slots past a run's last key)
     uint32_t cnt[kLsMaxSub + 32];
     uint32_t starts[kLsBatchIds + 1];
     uint32_t warp[kLsWarps];
     uint32_t red[2][kLsWarps];
     double dsum[kLsWarps];
     uint32_t ticket;
-    uint32_t cost;
+    uint32_t cost;     // sum of squares of the sub-bucket counts of the current run
+    uint32_t has_nan;  // the current run holds a NaN
 };
 
 struct LocalArgs {
@@ -415,13 +421,12 @@ __device__ __forceinline__ void scan_counts(LocalSmem& sm, int n_sub, int tid, i
     uint32_t c[PER];
     const int base = tid * PER;
     const bool on = base < n_sub;
-    if constexpr (PER == 8) {
-        const uint4 a = on ? *reinterpret_cast<const uint4*>(&sm.cnt[base]) : make_uint4(0, 0, 0, 0);
-        const uint4 b = on ? *reinterpret_cast<const uint4*>(&sm.cnt[base + 4]) : make_uint4(0, 0, 0, 0);
-        c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
-    } else if constexpr (PER == 4) {
-        const uint4 a = on ? *reinterpret_cast<const uint4*>(&sm.cnt[base]) : make_uint4(0, 0, 0, 0);
-        c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w;
+    if constexpr (PER >= 4) {
+#pragma unroll
+        for (int v = 0; v < PER / 4; ++v) {
+            const uint4 a = on ? *reinterpret_cast<const uint4*>(&sm.cnt[base + 4 * v]) : make_uint4(0, 0, 0, 0);
+            c[4 * v] = a.x, c[4 * v + 1] = a.y, c[4 * v + 2] = a.z, c[4 * v + 3] = a.w;
+        }
     } else if constexpr (PER == 2) {
         const uint2 a = on ? *reinterpret_cast<const uint2*>(&sm.cnt[base]) : make_uint2(0, 0);
         c[0] = a.x, c[1] = a.y;
@@ -448,11 +453,10 @@ __device__ __forceinline__ void scan_counts(LocalSmem& sm, int n_sub, int tid, i
 #pragma unroll
     for (int e = 0; e < PER; ++e) e0[e] = run, run += c[e];
     if (on) {
-        if constexpr (PER == 8) {
-            *reinterpret_cast<uint4*>(&sm.cnt[base]) = make_uint4(e0[0], e0[1], e0[2], e0[3]);
-            *reinterpret_cast<uint4*>(&sm.cnt[base + 4]) = make_uint4(e0[4], e0[5], e0[6], e0[7]);
-        } else if constexpr (PER == 4) {
-            *reinterpret_cast<uint4*>(&sm.cnt[base]) = make_uint4(e0[0], e0[1], e0[2], e0[3]);
+        if constexpr (PER >= 4) {
+#pragma unroll
+            for (int v = 0; v < PER / 4; ++v)
+                *reinterpret_cast<uint4*>(&sm.cnt[base + 4 * v]) = make_uint4(e0[4 * v], e0[4 * v + 1], e0[4 * v + 2], e0[4 * v + 3]);
         } else if constexpr (PER == 2) {
             *reinterpret_cast<uint2*>(&sm.cnt[base]) = make_uint2(e0[0], e0[1]);
         } else {
@@ -472,6 +476,7 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
     const int batches_per_seg = direct ? 1 : a.buckets / batch_ids;
     const uint32_t total = static_cast<uint32_t>(a.segments) * batches_per_seg;
     for (int i = tid; i < kLsMaxSub + 32; i += kLsThreads) sm.cnt[i] = 0;
+    if (tid == 0) sm.cost = 0, sm.has_nan = 0;
 
     double acc = 0.0;
     int acc_sum = -1;
@@ -533,10 +538,11 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
 
             // ---- keys -> registers; bounds of the run ----
             uint32_t k[kLsItems];  // raw float bits
+            {
+                const uint32_t* mine = src + tid;
+                const int left = n - tid;
 #pragma unroll
-            for (int q = 0; q < kLsItems; ++q) {
-                const int i = q * kLsThreads + tid;
-                k[q] = i < n ? __ldg(src + i) : 0u;
+                for (int q = 0; q < kLsItems; ++q) k[q] = q * kLsThreads < left ? __ldg(mine + q * kLsThreads) : 0u;
             }
             float flo, fhi;
             if (direct) {
@@ -567,7 +573,7 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
                 fhi = par.x + static_cast<float>(cs[end_id]) * cell_w;
             }
             int n_sub = 64;
-            while (n_sub < (n >> 1)) n_sub <<= 1;  // ~2 keys per sub-bucket, <= kLsMaxSub
+            while (n_sub < n) n_sub <<= 1;  // 0.5 .. 1 key per sub-bucket, <= kLsMaxSub
             const float scale = static_cast<float>(n_sub) / (fhi - flo);
             bool network = !(isfinite(flo) && isfinite(fhi) && fhi > flo);
             if (!network) {
@@ -576,13 +582,15 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
                 for (int q = 0; q < kLsItems; ++q) {
                     if (q * kLsThreads + tid < n) {
                         const int sub = linear_cell(k[q], flo, scale, n_sub);
+                        if (__uint_as_float(k[q]) != __uint_as_float(k[q])) sm.has_nan = 1;
                         pk[q] = (static_cast<uint32_t>(sub) << 16) | atomicAdd(&sm.cnt[sub], 1u);
                     }
                 }
-                if (tid == 0) sm.cost = 0;
                 __syncthreads();
                 // sum of squares of the counts = the compares the ranking step will make
-                if (n_sub >= 8 * kLsThreads)
+                if (n_sub >= 16 * kLsThreads)
+                    scan_counts<16>(sm, n_sub, tid, lane, warp);
+                else if (n_sub >= 8 * kLsThreads)
                     scan_counts<8>(sm, n_sub, tid, lane, warp);
                 else if (n_sub >= 4 * kLsThreads)
                     scan_counts<4>(sm, n_sub, tid, lane, warp);
@@ -592,25 +600,32 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
                     scan_counts<1>(sm, n_sub, tid, lane, warp);
                 if (tid == 0) sm.cnt[n_sub] = static_cast<uint32_t>(n);
                 // badly loaded sub-buckets (clustered values): the all-pairs ranking would cost more than the network
-                network = sm.cost > static_cast<uint32_t>(n) * 64u;
+                // (and a run with NaNs: the ranking step below assumes that u + 1 does not wrap and that values map to sub-buckets)
+                network = sm.cost > static_cast<uint32_t>(n) * 64u || sm.has_nan != 0;
                 __syncthreads();
                 if (!network) {
 #pragma unroll
                     for (int q = 0; q < kLsItems; ++q)
                         if (q * kLsThreads + tid < n) sm.buf[sm.cnt[pk[q] >> 16] + (pk[q] & 0xffff)] = float_to_ordered(k[q]);
+                    if (tid < 4) sm.buf[n + tid] = 0xffffffffu;
                     __syncthreads();
                     // slot order: lanes next to each other read the same few sub-buckets (broadcasts, neighbouring words) and
                     // write neighbouring final positions
                     for (int i = tid; i < n; i += kLsThreads) {
                         const uint32_t u = sm.buf[i];
                         const uint32_t bits = ordered_to_float(u);
-                        const int sub = linear_cell(bits, flo, scale, n_sub);
-                        const uint32_t s0 = sm.cnt[sub], s1 = sm.cnt[sub + 1];
+                        const int sub = linear_cell_finite(bits, flo, scale, n_sub);
+                        const uint32_t s0 = sm.cnt[sub], c = sm.cnt[sub + 1] - s0, self = static_cast<uint32_t>(i) - s0;
+                        // position = keys of the sub-bucket that sort before this one (ties: by slot).  Nearly every
+                        // sub-bucket holds <= 4 keys: four unconditional probes.  A probe past the sub-bucket's end meets
+                        // a key of a LATER sub-bucket (or the 0xffffffff behind the run), which is larger and counts nothing.
+                        // "<= for the slots before mine, < for those behind" as one unsigned compare against u or u + 1
+                        // (u + 1 cannot wrap: 0xffffffff is the image of a NaN, and runs with NaNs take the network)
                         uint32_t rank = s0;
-                        for (uint32_t j = s0; j < s1; ++j) {
-                            const uint32_t o = sm.buf[j];
-                            rank += (o < u || (o == u && j < static_cast<uint32_t>(i))) ? 1u : 0u;
-                        }
+                        const uint32_t* probe = sm.buf + s0;
+#pragma unroll
+                        for (uint32_t e = 0; e < 4; ++e) rank += probe[e] < u + (e < self ? 1u : 0u) ? 1u : 0u;
+                        for (uint32_t e = 4; e < c; ++e) rank += probe[e] < u + (e < self ? 1u : 0u) ? 1u : 0u;
                         emit(static_cast<int>(rank), bits);
                     }
                 }
@@ -630,6 +645,7 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
             }
             __syncthreads();
             for (int i = tid; i <= n_sub; i += kLsThreads) sm.cnt[i] = 0;  // ready for the next run
+            if (tid == 0) sm.cost = 0, sm.has_nan = 0;
             __syncthreads();
         }
     }
@@ -697,7 +713,7 @@ int sample_sort_launch(float* keys_device, int64_t rows, int segments, void* ws,
         ss_classify_kernel<<<dim3(ceil_div(p.blocks, kSsClsBlocks), segments), kSsThreads, p.cells * 2 + p.buckets * 4, stream>>>(
             keys, rows, p.buckets, p.blocks, lut, segpar, ids, counts);
         ss_scan_kernel<<<segments, kModelThreads, 0, stream>>>(counts, rows, p.buckets, p.blocks, starts, bases, ctrl);
-        ss_scatter_kernel<<<dim3(p.blocks, segments), kSsThreads, kScatterSmem, stream>>>(keys, ids, rows, p.buckets, p.blocks, counts, bases,
+        ss_scatter_kernel<<<dim3(p.blocks, segments), kScThreads, kScatterSmem, stream>>>(keys, ids, rows, p.buckets, p.blocks, counts, bases,
                                                                                          scratch, ctrl);
         a.src = scratch;
         a.buckets = p.buckets;

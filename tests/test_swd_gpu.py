@@ -175,6 +175,10 @@ def _sort_case(name, rs, segments, rows):
         k[:, ::7] = np.inf
         k[:, 3::11] = -np.inf
         return k
+    if name == "nans":  # positive NaNs sort last, as in np.sort
+        k = rs.randn(segments, rows).astype(np.float32)
+        k[:, ::13] = np.nan
+        return k
     if name == "denormals":
         return (rs.randn(segments, rows) * 1e-41).astype(np.float32)
     raise KeyError(name)
@@ -182,7 +186,7 @@ def _sort_case(name, rs, segments, rows):
 
 @pytest.mark.parametrize("rows", [5000, 70001, 300000])
 @pytest.mark.parametrize("name", ["all_equal", "ten_values", "ascending", "descending", "half_zero", "outliers", "clusters", "lognormal",
-                                  "nonfinite", "denormals"])
+                                  "nonfinite", "nans", "denormals"])
 def test_segmented_sort_is_exact_whatever_the_distribution(name, rows):
     """The bucket boundaries come from a sample of the keys and the sub-buckets from a linear map of the value: neither may
     cost correctness when the keys are nothing like a smooth density."""
