@@ -651,10 +651,20 @@ class _EventTimer:
         return len(self.pairs.get(name, []))
 
 
-# HBM bytes the radix sort moves per key (csrc/sort.cu): 4 digit passes x (histogram read + scatter read + write); in the
-# fused sort + |A - B| call the last pass over B reads the sorted A instead of writing (same count), and the separate
-# |A - B| pass (8 bytes per pair) no longer exists
+# HBM bytes a sort moves per key.  Radix passes (csrc/sort.cu): 4 digit passes x (histogram read + scatter read + write) = 48.
+# Value buckets (csrc/sort_sample.cu, segments of up to 2^21 keys): classify 4 + 2 (ids), scatter 4 + 2 + 4, local sort 4 + 4
+# = 24, plus the per-block bucket tables (6 bytes per (block of 16384 keys, bucket), written and read once).  In the fused
+# sort + |A - B| call the last step over B reads the sorted A instead of writing (same count).
 SORT_BYTES_PER_KEY = 48
+
+
+def sort_bytes_per_key(rows_per_segment, path):
+    if path != 2:
+        return float(SORT_BYTES_PER_KEY)
+    buckets = 2
+    while buckets * 2048 < rows_per_segment and buckets < 1024:
+        buckets *= 2
+    return 24.0 + 12.0 * buckets / 16384
 
 
 def swd_timing(n_images, dev, rank=0, world=1, hbm_peak=None):
@@ -722,6 +732,9 @@ def swd_timing(n_images, dev, rank=0, world=1, hbm_peak=None):
     rows = rounds * world * mb * 128                   # descriptors per level per set, whole job
     keys_job = 2 * 4 * 4 * 128 * rows                  # A and B, 4 levels, 512 directions (the zero real-vs-real pass is not counted)
     keys_rank = keys_job // world
+    from blurred_gan_b200 import _lib
+    sort_path = _lib.load().bgan_swd_sort_last_path()
+    bpk = sort_bytes_per_key(rows, sort_path)
     desc_bytes_job = 2 * 4 * rows * 147 * 4            # all-gather payload: every rank ends up with all of it
     out = {"images_per_set": rounds * world * mb, "n_gpus": world, "eval_s": round(total_s, 4), "feed_s": round(feed_s, 4),
            "end_s": round(total_s - feed_s, 4), "images_per_s": round(2 * rounds * world * mb / total_s, 1),
@@ -730,9 +743,11 @@ def swd_timing(n_images, dev, rank=0, world=1, hbm_peak=None):
            "sort": {"keys_whole_job": keys_job, "keys_per_rank": keys_rank, "sort_s": round(phases["swd_sort_diff_"], 4),
                     "gkeys_per_s_per_gpu": round(keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9, 2),
                     "gkeys_per_s_whole_job": round(keys_job / max(phases["swd_sort_diff_"], 1e-9) / 1e9, 2),
-                    "hbm_bytes_per_key": SORT_BYTES_PER_KEY,
-                    "hbm_gbs": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9, 1),
-                    "hbm_frac": round(SORT_BYTES_PER_KEY * keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9 / hbm_peak, 4) if hbm_peak else None},
+                    "keys_per_segment": rows,
+                    "path": {1: "radix passes", 2: "value buckets", 3: "value buckets gave up, radix passes"}.get(sort_path, str(sort_path)),
+                    "hbm_bytes_per_key": round(bpk, 2),
+                    "hbm_gbs": round(bpk * keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9, 1),
+                    "hbm_frac": round(bpk * keys_rank / max(phases["swd_sort_diff_"], 1e-9) / 1e9 / hbm_peak, 4) if hbm_peak else None},
            "note": "host RNG draws (reference order) are inside eval_s; device_time_s: CUDA-event pairs around the calls in a separate run; "
                    "swd_sort_diff_ = both sorts + the fused |A - B| sums (bgan_swd_sort_diff_f32)"}
     if world > 1:

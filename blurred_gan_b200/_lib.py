@@ -10,7 +10,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libbgan_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 RULE_TORCH, RULE_TF, RULE_EXPLICIT = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
@@ -38,6 +38,7 @@ SIGNATURES = {
     "bgan_swd_normalise_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_double, c_void_p]),
     "bgan_swd_project_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "bgan_swd_project_last_path": (c_int, []),
+    "bgan_swd_sort_last_path": (c_int, []),
     "bgan_swd_sort_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "bgan_swd_sort_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "bgan_swd_absdiff_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

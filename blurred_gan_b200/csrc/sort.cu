@@ -410,7 +410,11 @@ static int sort_passes(float* keys_device, int64_t rows, int segments, void* ws,
 // bucket that does not fit shared memory through a device flag and then has written nothing, so the fall-back starts from
 // the untouched keys; reading the flag costs one 4-byte device -> host copy (and a stream synchronisation) per call for
 // segments of more than 8192 keys.  A stream that is being captured cannot be synchronised: it takes the radix passes.
+static thread_local int g_sort_path = 0;
+extern "C" int bgan_swd_sort_last_path(void) { return g_sort_path; }
+
 static int sort_one(float* keys_device, int64_t rows, int segments, void* ws, cudaStream_t stream, const DiffArgs& da) {
+    g_sort_path = 1;
     if (use_sample_sort(rows)) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         BGAN_CUDA_OK(cudaStreamIsCapturing(stream, &cap));
@@ -418,11 +422,13 @@ static int sort_one(float* keys_device, int64_t rows, int segments, void* ws, cu
         if (cap == cudaStreamCaptureStatusNone || rows <= 8192) {
             const int rc = sample_sort_launch(keys_device, rows, segments, ws, stream, da, &flag_device);
             if (rc) return rc;
+            g_sort_path = 2;
             if (flag_device == nullptr) return 0;
             uint32_t flag = 0;
             BGAN_CUDA_OK(cudaMemcpyAsync(&flag, flag_device, sizeof(flag), cudaMemcpyDeviceToHost, stream));
             BGAN_CUDA_OK(cudaStreamSynchronize(stream));
             if (flag == 0) return 0;
+            g_sort_path = 3;
         }
     }
     return sort_passes(keys_device, rows, segments, ws, stream, da);

@@ -310,18 +310,25 @@ __global__ void __launch_bounds__(kModelThreads) ss_scan_kernel(const uint16_t* 
 }
 
 // ---- scatter -------------------------------------------------------------------------------------------------------------------
-constexpr size_t kScatterSmem = kSsBlock * sizeof(uint32_t) + kSsBlock * sizeof(uint16_t) + 2 * kSsMaxBuckets * sizeof(uint32_t) + 64;
+// Two ways out of shared memory.  RUNS: a group of lanes copies every bucket's run -- no id per slot, 72 KB, three CTAs per SM;
+// right when a block holds long runs (<= 512 buckets: >= 32 keys per run).  Otherwise every slot carries its bucket id and the
+// threads walk the slots (104 KB, two CTAs per SM): measured at 1024 buckets, 728 us against 826 us per 268 M keys.
+template <bool RUNS>
+constexpr size_t scatter_smem() {
+    return kSsBlock * sizeof(uint32_t) + (RUNS ? 0 : kSsBlock * sizeof(uint16_t)) + 2 * kSsMaxBuckets * sizeof(uint32_t) + 64;
+}
 
-__global__ void __launch_bounds__(kScThreads, 2) ss_scatter_kernel(const uint32_t* __restrict__ keys, const uint16_t* __restrict__ ids,
-                                                                   int64_t rows, int buckets, int blocks, const uint16_t* __restrict__ counts,
-                                                                   const uint32_t* __restrict__ bases, uint32_t* __restrict__ out,
-                                                                   const uint32_t* __restrict__ ctrl) {
+template <bool RUNS>
+__global__ void __launch_bounds__(kScThreads, RUNS ? 3 : 2) ss_scatter_kernel(const uint32_t* __restrict__ keys, const uint16_t* __restrict__ ids,
+                                                                             int64_t rows, int buckets, int blocks,
+                                                                             const uint16_t* __restrict__ counts, const uint32_t* __restrict__ bases,
+                                                                             uint32_t* __restrict__ out, const uint32_t* __restrict__ ctrl) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_key = reinterpret_cast<uint32_t*>(s_raw);
-    uint16_t* s_id = reinterpret_cast<uint16_t*>(s_raw + kSsBlock * sizeof(uint32_t));
-    uint32_t* s_cur = reinterpret_cast<uint32_t*>(s_raw + kSsBlock * (sizeof(uint32_t) + sizeof(uint16_t)));
+    uint32_t* s_cur = s_key + kSsBlock;  // first free local slot of a bucket; after the regrouping: the end of its run
     uint32_t* s_delta = s_cur + kSsMaxBuckets;
     uint32_t* s_warp = s_delta + kSsMaxBuckets;
+    uint16_t* s_id = reinterpret_cast<uint16_t*>(s_warp + 16);  // (!RUNS only)
     if (*ctrl != 0) return;
     const int blk = blockIdx.x, seg = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t row = (static_cast<size_t>(seg) * blocks + blk) * buckets;
@@ -361,6 +368,11 @@ __global__ void __launch_bounds__(kScThreads, 2) ss_scatter_kernel(const uint32_
     const size_t at = static_cast<size_t>(seg) * rows + base;
     const uint32_t* src = keys + at;
     const uint16_t* sid = ids + at;
+    auto put = [&](uint32_t id, uint32_t key) {
+        const uint32_t p = atomicAdd(&s_cur[id], 1u);
+        s_key[p] = key;
+        if constexpr (!RUNS) s_id[p] = static_cast<uint16_t>(id);
+    };
     int done = 0;
     if ((at & 3) == 0) {
         const int vec = valid >> 2;
@@ -368,24 +380,25 @@ __global__ void __launch_bounds__(kScThreads, 2) ss_scatter_kernel(const uint32_
         for (int v = tid; v < vec; v += kScThreads) {
             const uint4 k = __ldg(reinterpret_cast<const uint4*>(src) + v);
             const uint2 i2 = __ldg(reinterpret_cast<const uint2*>(sid) + v);
-            const uint32_t id0 = i2.x & 0xffff, id1 = i2.x >> 16, id2 = i2.y & 0xffff, id3 = i2.y >> 16;
-            const uint32_t p0 = atomicAdd(&s_cur[id0], 1u), p1 = atomicAdd(&s_cur[id1], 1u);
-            const uint32_t p2 = atomicAdd(&s_cur[id2], 1u), p3 = atomicAdd(&s_cur[id3], 1u);
-            s_key[p0] = k.x, s_id[p0] = static_cast<uint16_t>(id0);
-            s_key[p1] = k.y, s_id[p1] = static_cast<uint16_t>(id1);
-            s_key[p2] = k.z, s_id[p2] = static_cast<uint16_t>(id2);
-            s_key[p3] = k.w, s_id[p3] = static_cast<uint16_t>(id3);
+            put(i2.x & 0xffff, k.x);
+            put(i2.x >> 16, k.y);
+            put(i2.y & 0xffff, k.z);
+            put(i2.y >> 16, k.w);
         }
         done = vec << 2;
     }
-    for (int i = done + tid; i < valid; i += kScThreads) {
-        const uint32_t id = sid[i], p = atomicAdd(&s_cur[id], 1u);
-        s_key[p] = __ldg(src + i), s_id[p] = static_cast<uint16_t>(id);
-    }
+    for (int i = done + tid; i < valid; i += kScThreads) put(sid[i], __ldg(src + i));
     __syncthreads();
     uint32_t* dst = out + static_cast<size_t>(seg) * rows;
+    if constexpr (RUNS) {
+        for (int id = warp; id < buckets; id += kScThreads / 32) {
+            const uint32_t ls = id ? s_cur[id - 1] : 0u, le = s_cur[id], d = s_delta[id];
+            for (uint32_t slot = ls + lane; slot < le; slot += 32) dst[d + slot] = s_key[slot];
+        }
+    } else {
 #pragma unroll 4
-    for (int slot = tid; slot < valid; slot += kScThreads) dst[s_delta[s_id[slot]] + slot] = s_key[slot];
+        for (int slot = tid; slot < valid; slot += kScThreads) dst[s_delta[s_id[slot]] + slot] = s_key[slot];
+    }
 }
 
 // ---- local sort ------------------------------------------------------------------------------------------------------------------
@@ -525,11 +538,13 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
             g0 = g1;
             if (n == 0) continue;
             const uint32_t* src = a.src + seg_at + start;
+            const float* const ref_run = DIFF ? a.da.ref + seg_at + start : nullptr;
+            uint32_t* const dst_run = DIFF ? nullptr : a.dst + seg_at + start;
             auto emit = [&](int pos, uint32_t float_bits) {  // the key whose final position in the run is `pos`
                 if constexpr (DIFF)
-                    acc += static_cast<double>(fabsf(__ldg(a.da.ref + seg_at + start + pos) - __uint_as_float(float_bits)));
+                    acc += static_cast<double>(fabsf(__ldg(ref_run + pos) - __uint_as_float(float_bits)));
                 else
-                    a.dst[seg_at + start + pos] = float_bits;
+                    dst_run[pos] = float_bits;
             };
             if (n > kSsCap) {  // (cannot happen: the scan kernel raised the flag and nothing runs)
                 for (int i = tid; i < n; i += kLsThreads) emit(i, __ldg(src + i));
@@ -581,8 +596,11 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
 #pragma unroll
                 for (int q = 0; q < kLsItems; ++q) {
                     if (q * kLsThreads + tid < n) {
-                        const int sub = linear_cell(k[q], flo, scale, n_sub);
-                        if (__uint_as_float(k[q]) != __uint_as_float(k[q])) sm.has_nan = 1;
+                        int sub = linear_cell_finite(k[q], flo, scale, n_sub);
+                        if (__uint_as_float(k[q]) != __uint_as_float(k[q])) {  // (the run then takes the network below)
+                            sub = 0;
+                            sm.has_nan = 1;
+                        }
                         pk[q] = (static_cast<uint32_t>(sub) << 16) | atomicAdd(&sm.cnt[sub], 1u);
                     }
                 }
@@ -619,13 +637,13 @@ __global__ void __launch_bounds__(kLsThreads, 2) ss_local_sort_kernel(const Loca
                         // position = keys of the sub-bucket that sort before this one (ties: by slot).  Nearly every
                         // sub-bucket holds <= 4 keys: four unconditional probes.  A probe past the sub-bucket's end meets
                         // a key of a LATER sub-bucket (or the 0xffffffff behind the run), which is larger and counts nothing.
-                        // "<= for the slots before mine, < for those behind" as one unsigned compare against u or u + 1
-                        // (u + 1 cannot wrap: 0xffffffff is the image of a NaN, and runs with NaNs take the network)
+                        // "<= for the slots before mine, < for those behind" is one 64-bit compare of (key, slot) pairs
                         uint32_t rank = s0;
                         const uint32_t* probe = sm.buf + s0;
+                        const uint64_t mine = (static_cast<uint64_t>(u) << 32) | self;
 #pragma unroll
-                        for (uint32_t e = 0; e < 4; ++e) rank += probe[e] < u + (e < self ? 1u : 0u) ? 1u : 0u;
-                        for (uint32_t e = 4; e < c; ++e) rank += probe[e] < u + (e < self ? 1u : 0u) ? 1u : 0u;
+                        for (uint32_t e = 0; e < 4; ++e) rank += ((static_cast<uint64_t>(probe[e]) << 32) | e) < mine ? 1u : 0u;
+                        for (uint32_t e = 4; e < c; ++e) rank += ((static_cast<uint64_t>(probe[e]) << 32) | e) < mine ? 1u : 0u;
                         emit(static_cast<int>(rank), bits);
                     }
                 }
@@ -681,7 +699,8 @@ int sample_sort_launch(float* keys_device, int64_t rows, int segments, void* ws,
     if (attr_dev != dev) {
         BGAN_CUDA_OK(cudaFuncSetAttribute(ss_model_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsMaxCells * 4));
         BGAN_CUDA_OK(cudaFuncSetAttribute(ss_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsMaxCells * 2 + kSsMaxBuckets * 4));
-        BGAN_CUDA_OK(cudaFuncSetAttribute(ss_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kScatterSmem)));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(ss_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem<true>())));
+        BGAN_CUDA_OK(cudaFuncSetAttribute(ss_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem<false>())));
         BGAN_CUDA_OK(cudaFuncSetAttribute(ss_local_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LocalSmem))));
         BGAN_CUDA_OK(cudaFuncSetAttribute(ss_local_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(LocalSmem))));
         attr_dev = dev;
@@ -713,8 +732,12 @@ int sample_sort_launch(float* keys_device, int64_t rows, int segments, void* ws,
         ss_classify_kernel<<<dim3(ceil_div(p.blocks, kSsClsBlocks), segments), kSsThreads, p.cells * 2 + p.buckets * 4, stream>>>(
             keys, rows, p.buckets, p.blocks, lut, segpar, ids, counts);
         ss_scan_kernel<<<segments, kModelThreads, 0, stream>>>(counts, rows, p.buckets, p.blocks, starts, bases, ctrl);
-        ss_scatter_kernel<<<dim3(p.blocks, segments), kScThreads, kScatterSmem, stream>>>(keys, ids, rows, p.buckets, p.blocks, counts, bases,
-                                                                                         scratch, ctrl);
+        if (p.buckets <= 512)
+            ss_scatter_kernel<true><<<dim3(p.blocks, segments), kScThreads, scatter_smem<true>(), stream>>>(keys, ids, rows, p.buckets, p.blocks,
+                                                                                                           counts, bases, scratch, ctrl);
+        else
+            ss_scatter_kernel<false><<<dim3(p.blocks, segments), kScThreads, scatter_smem<false>(), stream>>>(keys, ids, rows, p.buckets, p.blocks,
+                                                                                                             counts, bases, scratch, ctrl);
         a.src = scratch;
         a.buckets = p.buckets;
         a.starts = starts;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BGAN_ABI_VERSION 3 /* 2: + bgan_blur2d_multi_f32, bgan_lerp_rows_f32, bgan_swd_feed_f32; 3: + bgan_swd_sort_diff_f32 */
+#define BGAN_ABI_VERSION 4 /* 2: + bgan_blur2d_multi_f32, bgan_lerp_rows_f32, bgan_swd_feed_f32; 3: + bgan_swd_sort_diff_f32; 4: + bgan_swd_sort_last_path */
 
 /* tap rules */
 #define BGAN_RULE_TORCH 0    /* pytorch/gaussianblur.py:9-14 (normaliser inside the exp)  */
@@ -147,10 +147,19 @@ int bgan_swd_project_f32(const float* desc_device, int64_t rows, int k, const fl
  * (error-compensated fp16 split, k <= 192). */
 int bgan_swd_project_last_path(void);
 
-/* sliced_wasserstein.py:47-48  ascending sort of each of the `segments` contiguous runs of `rows`
- * floats, in place (LSD radix sort; ws from the query below). */
+/* sliced_wasserstein.py:47-48  ascending sort of each of the `segments` contiguous runs of `rows` floats, in place (ws
+ * from the query below).  The order is that of the floats' order-preserving uint32 images: -0 before +0, NaNs with the sign
+ * bit clear last (as np.sort), NaNs with the sign bit set first.
+ * Segments of up to 2^21 keys are sorted by value buckets in shared memory (two passes over HBM: csrc/sort_sample.cu);
+ * longer segments, and inputs whose values are so unevenly spread that a bucket does not fit a CTA (outliers tens of
+ * standard deviations out, one value repeated thousands of times), by four LSD radix passes (csrc/sort.cu).  The second
+ * case is detected on the device: for segments of more than 8192 keys the call therefore reads one 4-byte flag back and
+ * SYNCHRONISES THE STREAM before it returns (a stream that is being captured takes the radix passes, which never do). */
 size_t bgan_swd_sort_workspace_bytes(int64_t rows, int segments);
 int bgan_swd_sort_f32(float* keys_device, int64_t rows, int segments, void* ws_device, size_t ws_bytes, void* stream);
+/* How the last sort (bgan_swd_sort_f32, or the second sort of bgan_swd_sort_diff_f32) on this thread was executed:
+ * 1 = LSD radix passes, 2 = value buckets, 3 = value buckets gave up (flag) and the radix passes did the work. */
+int bgan_swd_sort_last_path(void);
 
 /* sliced_wasserstein.py:49-50  *sum_out_device += sum_i |a[i] - b[i]| (fp64; caller zeroes it). */
 int bgan_swd_absdiff_sum_f32(const float* a_device, const float* b_device, int64_t count, double* sum_out_device,
@@ -158,9 +167,9 @@ int bgan_swd_absdiff_sum_f32(const float* a_device, const float* b_device, int64
 
 /* sliced_wasserstein.py:47-50 as ONE call: sort every segment of a_device in place (ascending), sort the segments of
  * b_device, and add sum_i |sort(a)[i] - sort(b)[i]| of segment s to sums_device[(s + seg_offset) / segs_per_sum] (fp64,
- * accumulated into; n_sums entries).  The last radix pass over b does not write the keys: every key meets the element of the
- * sorted a that sits at its final position and only the distance is accumulated -- the sorted b is never stored and the
- * separate |a - b| pass disappears.  b_device is clobbered (partially sorted on return).  a and b: `segments` contiguous
+ * accumulated into; n_sums entries).  The last step of the sort of b does not write the keys: every key meets the element of
+ * the sorted a that sits at its final position and only the distance is accumulated -- the sorted b is never stored and the
+ * separate |a - b| pass disappears.  b_device is clobbered (unspecified contents on return).  a and b: `segments` contiguous
  * runs of `rows` floats.  seg_offset / segs_per_sum: a rank that owns directions [seg_offset, seg_offset + segments) of the
  * dir_repeats x dirs_per_repeat matrix passes segs_per_sum = dirs_per_repeat and gets one sum per repeat. */
 size_t bgan_swd_sort_diff_workspace_bytes(int64_t rows, int segments, int n_sums);

@@ -128,7 +128,7 @@ def test_projection_long_descriptors_use_the_fma_kernel():
 def test_segmented_sort_is_exact(segments, rows, algo, monkeypatch):
     """Three routes: the splitter / shared-memory-bucket sort (segments of up to 2^21 keys), the radix passes alone, and the
     radix passes entered through the sample sort's overflow flag."""
-    from blurred_gan_b200 import ops
+    from blurred_gan_b200 import _lib, ops
 
     if algo == "lsd":
         monkeypatch.setenv("BGAN_SORT_ALGO", "lsd")
@@ -145,6 +145,15 @@ def test_segmented_sort_is_exact(segments, rows, algo, monkeypatch):
     got = ops.swd_sort_(_dev(keys)).cpu().numpy()
     want = np.sort(keys, axis=1)
     np.testing.assert_array_equal(got, want)  # (-0.0 == 0.0 compares equal; order among them is irrelevant)
+    path = _lib.load().bgan_swd_sort_last_path()
+    if algo == "lsd" or rows > (1 << 21):
+        assert path == 1
+    elif rows <= 8192:
+        assert path == 2  # one CTA per segment: nothing can overflow, nothing is read back
+    elif algo == "fallback":
+        assert path == 3
+    else:
+        assert path in (2, 3)  # (3: an infinity among the samples stretches the value range)
 
 
 def _sort_case(name, rs, segments, rows):
@@ -190,12 +199,17 @@ def _sort_case(name, rs, segments, rows):
 def test_segmented_sort_is_exact_whatever_the_distribution(name, rows):
     """The bucket boundaries come from a sample of the keys and the sub-buckets from a linear map of the value: neither may
     cost correctness when the keys are nothing like a smooth density."""
-    from blurred_gan_b200 import ops
+    from blurred_gan_b200 import _lib, ops
 
     rs = np.random.RandomState(rows + len(name))
     keys = _sort_case(name, rs, 3, rows)
     got = ops.swd_sort_(_dev(keys)).cpu().numpy()
     np.testing.assert_array_equal(got, np.sort(keys, axis=1))
+    path = _lib.load().bgan_swd_sort_last_path()
+    if rows > 8192 and name in ("ascending", "descending"):
+        assert path == 2  # smooth densities stay on the value-bucket route
+    if rows > 8192 and name in ("all_equal", "half_zero"):
+        assert path == 3  # one value (or one cell) holds more keys than a CTA: flag, radix passes
 
 
 def test_absdiff_sum():
