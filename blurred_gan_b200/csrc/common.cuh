@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 
 #include "bgan.h"
 
@@ -51,6 +52,14 @@ static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 // ---- device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch, used as "the same stream order, minus the launch gap": a kernel launched with launch_pdl may be
+// scheduled while its predecessor in the stream is still running; pdl_wait() at its top (before its first global access) blocks
+// until the predecessor has completed and its writes are visible.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -156,6 +165,23 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+// host side of pdl_wait(): launch with programmatic stream serialization allowed
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 #endif  // __CUDACC__

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__
                                                        int ow) {
     const unsigned total = static_cast<unsigned>(planes) * oh * ow;
     const bool small = H < 3 || W < 3;
+    pdl_wait();
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const unsigned r = idx / static_cast<unsigned>(ow);
         const int ox = static_cast<int>(idx - r * ow);
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(const float* __restrict__ x
     const int OH = 2 * h, OW = 2 * w;
     const unsigned total = static_cast<unsigned>(planes) * OH * OW;
     const bool small = OH < 3 || OW < 3;
+    pdl_wait();
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const unsigned r = idx / static_cast<unsigned>(OW);
         const int X = static_cast<int>(idx - r * OW);
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) pyr_up_quad_kernel(const float* __restric
                                                           int planes, int h, int w) {
     const unsigned total = static_cast<unsigned>(planes) * h * w;
     const int OW = 2 * w;
+    pdl_wait();
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const unsigned r = idx / static_cast<unsigned>(w);
         const int b = static_cast<int>(idx - r * w);
@@ -168,6 +171,7 @@ __device__ __forceinline__ void extract_body(const float* __restrict__ level, in
     const int64_t step = static_cast<int64_t>(gridDim.x) * warps;
     int64_t m = static_cast<int64_t>(blockIdx.x) * warps + warp;
     int y_next = 0, x_next = 0;
+    pdl_wait();  // (the descriptor geometry above overlaps the tail of the pyramid kernel before this one)
     if (m < n_desc) {
         y_next = __ldg(py + m);
         x_next = __ldg(px + m);
@@ -419,8 +423,8 @@ extern "C" int bgan_pyr_down_f32(const float* x, float* y, int planes, int heigh
     const int oh = (height + 1) / 2, ow = (width + 1) / 2;
     const int64_t total = static_cast<int64_t>(planes) * oh * ow;
     BGAN_REQUIRE(static_cast<int64_t>(planes) * height * width < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_pyr_down_f32: more than 2^31 pixels per call");
-    pyr_down_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, planes, height, width, oh, ow);
-    BGAN_LAUNCH_OK();
+    BGAN_CUDA_OK(launch_pdl(pyr_down_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, y, planes, height,
+                            width, oh, ow));
     return 0;
 }
 
@@ -430,10 +434,11 @@ extern "C" int bgan_pyr_up_f32(const float* x, const float* minuend, float* y, i
     BGAN_REQUIRE(total < (int64_t(1) << 31), BGAN_E_BADARG, "bgan_pyr_up_f32: more than 2^31 pixels per call");
     const bool aligned8 = reinterpret_cast<uintptr_t>(y) % 8 == 0 && (minuend == nullptr || reinterpret_cast<uintptr_t>(minuend) % 8 == 0);
     if (h >= 2 && w >= 2 && aligned8)
-        pyr_up_quad_kernel<<<grid_for(total / 4, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, minuend, y, planes, h, w);
+        BGAN_CUDA_OK(launch_pdl(pyr_up_quad_kernel, dim3(grid_for(total / 4, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, minuend, y,
+                                planes, h, w));
     else
-        pyr_up_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, minuend, y, planes, h, w);
-    BGAN_LAUNCH_OK();
+        BGAN_CUDA_OK(launch_pdl(pyr_up_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, minuend, y, planes, h,
+                                w));
     return 0;
 }
 
@@ -526,8 +531,8 @@ extern "C" int bgan_swd_feed_f32(const float* minibatch, int n, int c, int h, in
     }
     if (fused_gather) {  // :13-23 for every level
         const int64_t ctas = std::min<int64_t>(ceil_div64(count, 8), 2 * static_cast<int64_t>(device_sm_count()));
-        extract_levels_kernel<4, 5><<<dim3(static_cast<unsigned>(ctas), levels), 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, c, nhoods_per_image, nhood, count);
-        BGAN_LAUNCH_OK();
+        BGAN_CUDA_OK(launch_pdl(extract_levels_kernel<4, 5>, dim3(static_cast<unsigned>(ctas), levels), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                lv, c, nhoods_per_image, nhood, count));
     }
     return 0;
 }
