@@ -698,9 +698,15 @@ int blur2d_dispatch(const MultiIO& io, const Geometry& g, int rule, float std_ef
     }
     // the unit counters of the one-launch kernels are 32-bit
     const bool one_launch = static_cast<int64_t>(g.planes) * g.ES * io.count * 2 < (int64_t(1) << 31);
-    // 128 x 128 planes: the FFMA kernel up to radius 4 (HBM-bound there); radius 5 costs it 26.8 us per 768 planes against the
-    // tensor-core kernel's 24.7, so it only keeps radius 5 for explicit taps (which the tensor-core kernel does not take)
-    if (one_launch && direct_ok && !(tc_ok && radius >= 5)) {
+    // 128 x 128 planes: the FFMA kernel up to radius 5 -- HBM-bound up to 4 (18.8 - 19.6 us per 768 planes), 22.7 us at 5, 24.6 at 6,
+    // 28.9 at 7 against 25 - 26.7 for the tensor-core kernel (plain stream; round 2, after the taps became uniform operands and
+    // the planes half-plane units: csrc/blur_direct.cu).  Radii 6 .. 8 only for explicit taps (which the tensor-core kernel does
+    // not take).
+    static const int direct_cut = [] {  // first radius that goes to the tensor-core kernel when both kernels take the call
+        const char* e = getenv("BGAN_BLUR_DIRECT_CUT");
+        return e ? atoi(e) : 6;
+    }();
+    if (one_launch && direct_ok && !(tc_ok && radius >= direct_cut)) {
         g_last_path = 5;
         return blur_direct_launch(io, g.planes, g.ES, radius, rule, std_eff, taps_device, stream);
     }

@@ -94,7 +94,7 @@ int bgan_lerp_rows_f32(const float* u_device, const float* v_device, const float
 
 /* How the last bgan_blur2d_f32 / bgan_blur2d_multi_f32 call on this thread was executed: 1 = fused tile kernel with TMA
  * staging, 2 = fused tile kernel with plain loads, 3 = two launches (row pass, column pass), 4 = tcgen05 tensor-core kernel (128 x 128 planes),
- * 5 = direct FFMA kernel for 128 x 128 images with radius <= 4 (radius 5 only with caller-supplied taps), 6 = two-pass tcgen05 kernel for planes of
+ * 5 = direct FFMA kernel for 128 x 128 images with radius <= 5 NCHW / <= 4 NHWC (NCHW radius 6 .. 8 only with caller-supplied taps), 6 = two-pass tcgen05 kernel for planes of
  * 256 x 256 and more with radius 12 .. 256 (needs the workspace), 7 = the same for NHWC images with 2 .. 4 channels:
  * interleaved -> planar copy, path 6 on the channel planes, planar -> interleaved (needs the workspace). */
 int bgan_blur2d_last_path(void);
