@@ -313,7 +313,7 @@ def run_native(args, stds):
     launches = args.steps * len(stds) * 2
 
     KERNELS = {4: "blur_tc128_kernel (tcgen05 Toeplitz GEMMs, TMEM accumulators, TMA staged)",
-               5: "blur_direct128_kernel (FFMA, TMA staged, register-resident separable passes; radius <= 4)"}
+               5: "blur_direct128_kernel (FFMA, TMA staged, register-resident separable passes; radius <= 5)"}
     per_std = []
     for j, s in enumerate(stds):
         ms = statistics.mean(ev[i][j][0].elapsed_time(ev[i][j][1]) for i in range(reps))
