@@ -181,6 +181,44 @@ def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
 
 
+class Gathered:
+    """The result of `all_gather_rows_async`: `.result()` makes the current stream (NCCL) or the host (gloo) wait for the
+    collective and returns the gathered tensor.  Until then the collective runs beside whatever is enqueued on the
+    compute stream -- the kernels of the next `feed` calls, the sort of the previous pyramid level."""
+
+    def __init__(self, out: torch.Tensor, work=None, keep=None):
+        self._out, self._work, self._keep = out, work, keep
+
+    def result(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = self._keep = None
+        return self._out
+
+
+def all_gather_rows_async(t: torch.Tensor, group=None, equal_rows: bool = False) -> Gathered:
+    """`all_gather_rows` that does not wait: equal shards over NCCL are gathered with `async_op=True` (the collective runs on
+    NCCL's own stream, ordered after what the current stream holds at this point); every other case is gathered at once.
+    `equal_rows`: the caller knows that every rank holds the same number of rows (`API.end` after its lock-step check) --
+    otherwise the row counts are exchanged first, and reading them back waits for everything NCCL's stream still holds."""
+    rank, world = world_info(group)
+    if world == 1 or _needs_host_staging(t, group) or not t.is_cuda:
+        return Gathered(all_gather_rows(t, group))
+    t = t.contiguous()
+    if equal_rows:
+        sizes = [t.shape[0]] * world
+    else:
+        counts = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        all_counts = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(all_counts, counts, group=group)
+        sizes = [int(c.item()) for c in all_counts]
+    if len(set(sizes)) != 1:
+        return Gathered(all_gather_rows(t, group))
+    out = torch.empty((sizes[0] * world,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    work = dist.all_gather_into_tensor(out, t, group=group, async_op=True)
+    return Gathered(out, work, keep=t)
+
+
 def combine_repeat_sums(partial: torch.Tensor, rows: int, dirs_per_repeat: int, group=None) -> float:
     """partial[r] = this rank's sum of |sorted A - sorted B| over its directions of repeat r (fp64).  Returns the
     reference's `np.mean` over repeats of the per-repeat fp32 means (sliced_wasserstein.py:49-51)."""

@@ -194,7 +194,11 @@ class API:
     ``distributed=True``).  Every rank feeds its own shard of the images; see ``blurred_gan_b200/dist.py`` for the
     exchange and for how the random stream stays identical to a single-process run."""
 
-    def __init__(self, image_shape, device=None, group=None, distributed=False):
+    def __init__(self, image_shape, device=None, group=None, distributed=False, overlap_gather=True):
+        # overlap_gather: the all-gathers of `end` run asynchronously (NCCL's stream) beside the next set's feed kernels and the
+        # previous level's sort; False waits for each one on the spot (bench.py's per-phase device times)
+        self.overlap_gather = overlap_gather
+        self._desc_real = None
         self.nhood_size, self.nhoods_per_image = 7, 128
         self.dir_repeats, self.dirs_per_repeat = 4, 128
         self.device = device
@@ -272,13 +276,30 @@ class API:
             self.descriptors[lod].append(ops.swd_extract(level, px, py, self.nhoods_per_image, self.nhood_size, self._sums[lod][: 2 * c]))
             self._rows[lod] += count
 
-    def _finalize(self, desc, sums, rows_local):
-        """Standardise with the statistics of the whole (all-rank) set, then gather every rank's rows."""
-        sums[-1] = float(rows_local)
-        _dist.all_reduce_sum_(sums, self.group)
-        rows_total = sums[-1:].cpu().item()  # exact in fp64
-        ops.swd_normalise_(desc, sums, rows_total * desc.shape[2] * desc.shape[3])
-        return _dist.all_gather_rows(desc.reshape(desc.shape[0], -1), self.group)
+    def _finalize_all(self, local):
+        """Standardise every level with the statistics of the whole (all-rank) set, then gather every rank's rows.  One
+        all-reduce for the sums of all levels and one read-back of the row counts, BEFORE the first gather is enqueued: a
+        read-back behind a gather would wait for it and the gathers could not run beside anything."""
+        for sums, rows_local in zip(self._sums, self._rows):
+            sums[-1] = float(rows_local)
+        stacked = torch.stack(self._sums)  # [levels, 2 C + 1]
+        _dist.all_reduce_sum_(stacked, self.group)
+        rows_total = stacked[:, -1].cpu().tolist()  # exact in fp64
+        out = []
+        for lod, desc in enumerate(local):
+            ops.swd_normalise_(desc, stacked[lod], rows_total[lod] * desc.shape[2] * desc.shape[3])
+            flat = desc.reshape(desc.shape[0], -1)
+            if self.overlap_gather:
+                # (equal row counts on every rank: check_lockstep in end() has just verified the feed counts and sizes)
+                out.append(_dist.all_gather_rows_async(flat, self.group, equal_rows=True))
+            else:
+                out.append(_dist.Gathered(_dist.all_gather_rows(flat, self.group)))
+        return out
+
+    @property
+    def desc_real(self):
+        """The standardised descriptors of the real set, one [rows, 147] tensor per level (waits for their all-gathers)."""
+        return None if self._desc_real is None else [g.result() for g in self._desc_real]
 
     def end(self, mode):
         # every rank replays the position draws of all ranks with its OWN minibatch sizes (dist.positions_packed_for_round):
@@ -289,21 +310,24 @@ class API:
             local = [slab[:rows] if 4 * rows >= 3 * slab.shape[0] else slab[:rows].clone() for slab, rows in zip(self._slabs, self._rows)]
         else:
             local = [chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=0) for chunks in self.descriptors]
-        desc = [self._finalize(d, s, r) for d, s, r in zip(local, self._sums, self._rows)]
+        local_dlen = int(local[0].shape[1] * local[0].shape[2] * local[0].shape[3])
+        desc = self._finalize_all(local)
         del self.descriptors, local
         self._slabs = None
         if mode in ['warmup', 'reals']:
-            self.desc_real = desc
+            self._desc_real = desc  # (not waited for: the gathers overlap the feed of the next set)
             # The reference evaluates sliced_wasserstein(real, real) here: dir_repeats randn draws per level and
             # a result of exactly 0.  Consume the draws (they position the stream for the fakes), skip the sorts.
-            for d in desc:
+            dlen = local_dlen
+            for _ in desc:
                 for _ in range(self.dir_repeats):
-                    np.random.randn(d.shape[1], self.dirs_per_repeat)
+                    np.random.randn(dlen, self.dirs_per_repeat)
             dist = [np.float32(0.0)] * len(desc)
         else:
             scratch = {}  # projections + sort workspace, shared by the levels of this evaluation
-            dist = [sliced_wasserstein(real, fake, self.dir_repeats, self.dirs_per_repeat, self.group, scratch)
-                    for real, fake in zip(self.desc_real, desc)]
+            # level by level: wait for this level's two gathers only -- the later levels' gathers run beside its sort
+            dist = [sliced_wasserstein(real.result(), fake.result(), self.dir_repeats, self.dirs_per_repeat, self.group, scratch)
+                    for real, fake in zip(self._desc_real, desc)]
             del scratch
         scaled = [d * 1e3 for d in dist]
         return scaled + [np.mean(scaled)]

@@ -39,6 +39,11 @@ def _worker(rank, world, port, out_dir):
     t = torch.full((3 + rank, 2), float(rank))
     g = bd.all_gather_rows(t)
     assert g.shape == (3 + 4, 2) and torch.equal(g[:3], torch.zeros(3, 2)) and torch.equal(g[3:], torch.ones(4, 2))
+    # the asynchronous form: CPU / gloo tensors are gathered at once, equal or not; the handle returns the same tensor every time
+    for rows in (3 + rank, 5):
+        h = bd.all_gather_rows_async(torch.full((rows, 2), float(rank)), equal_rows=(rows == 5))
+        got = h.result()
+        assert got is h.result() and torch.equal(got, bd.all_gather_rows(torch.full((rows, 2), float(rank))))
     # ---- lock-step check: equal feed logs pass, a rank that fed another minibatch size is caught on every rank ----
     bd.check_lockstep([3, 12345])
     try:

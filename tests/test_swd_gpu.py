@@ -156,6 +156,28 @@ def test_segmented_sort_is_exact(segments, rows, algo, monkeypatch):
         assert path in (2, 3)  # (3: an infinity among the samples stretches the value range)
 
 
+def test_sort_inside_a_cuda_graph_takes_the_radix_passes():
+    """The value-bucket sort reads an overflow flag back and synchronises the stream; a stream that is being captured cannot be
+    synchronised, so a captured sort of long segments must run the radix passes (and replay correctly)."""
+    from blurred_gan_b200 import _lib, ops
+
+    rs = np.random.RandomState(77)
+    src = torch.from_numpy(rs.randn(3, 50000).astype(np.float32)).cuda()
+    keys = src.clone()
+    scratch = {}
+    ops.swd_sort_(keys.clone(), scratch)  # workspace allocated outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.swd_sort_(keys, scratch)
+    assert _lib.load().bgan_swd_sort_last_path() == 1
+    for _ in range(2):
+        keys.copy_(src)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(keys, torch.sort(src, dim=1).values)
+
+
 def _sort_case(name, rs, segments, rows):
     if name == "all_equal":
         return np.full((segments, rows), 0.25, np.float32)

@@ -1,4 +1,4 @@
-"""Time the segmented radix sort (CUDA events): python tools/sort_bench.py [segments] [rows]"""
+"""Time the segmented sort (CUDA events): python tools/sort_bench.py [segments] [rows]   (BGAN_SORT_ALGO=lsd: radix passes only)"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
