@@ -1,6 +1,8 @@
 """GPU parity tests of the SWD kernels against the CPU oracle and the reference's golden vectors.
 Integer / gather / sort work is bit-exact; the pyramid is bit-exact (fp64 accumulate, one rounding);
 floating-point reductions are within 1e-6; the SWD distances within north_star's 1e-4."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -176,6 +178,17 @@ def test_sort_inside_a_cuda_graph_takes_the_radix_passes():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(keys, torch.sort(src, dim=1).values)
+
+
+def test_sort_fuzz_short():
+    """Ten seconds of tools/sort_fuzz.py: random shapes (ragged blocks, runs at the 8192-key boundary, odd row counts) and
+    distributions through the sort and the fused sort + distance, against torch.sort and fp64 sums."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "tools", "sort_fuzz.py"), "10", "3"], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0 and proc.stdout.startswith("ok:"), proc.stdout + proc.stderr
 
 
 def _sort_case(name, rs, segments, rows):
