@@ -34,12 +34,12 @@ __device__ __forceinline__ int mirror101_near(int i, int n, bool small) {
     return i < n ? i : 2 * (n - 1) - i;
 }
 
-__global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int oh,
-                                                       int ow) {
+// (vblock of vgrid: the block's place in the grid-stride loop -- a launch may run two bodies side by side, see pyr_pair_kernel)
+__device__ __forceinline__ void pyr_down_body(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int oh, int ow,
+                                              unsigned vblock, unsigned vgrid) {
     const unsigned total = static_cast<unsigned>(planes) * oh * ow;
     const bool small = H < 3 || W < 3;
-    pdl_wait();
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    for (unsigned idx = vblock * blockDim.x + threadIdx.x; idx < total; idx += vgrid * blockDim.x) {
         const unsigned r = idx / static_cast<unsigned>(ow);
         const int ox = static_cast<int>(idx - r * ow);
         const unsigned p = r / static_cast<unsigned>(oh);
@@ -59,6 +59,12 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__
         }
         y[idx] = static_cast<float>(acc * (1.0 / 256.0));
     }
+}
+
+__global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int H, int W, int oh,
+                                                       int ow) {
+    pdl_wait();
+    pyr_down_body(x, y, planes, H, W, oh, ow, blockIdx.x, gridDim.x);
 }
 
 // y[p, Y, X] = (minuend ? minuend[p, Y, X] : 0) -/+ sum 4 B5 B5 / 256 * Z[m(Y+dy-2), m(X+dx-2)],
@@ -100,12 +106,11 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(const float* __restrict__ x
 // 1, 6, 1 and an odd one the rows a, a + 1 with weights 4, 4 (columns alike); REFLECT_101 on the zero-stuffed grid keeps the
 // parity of an index, so at the borders row -1 becomes row 1 and row h becomes row h - 1.  Same products, same exact fp64
 // sums, hence the same bits as pyr_up_kernel -- with 9 loads per four outputs instead of ~25, and 8-byte stores.
-__global__ void __launch_bounds__(256) pyr_up_quad_kernel(const float* __restrict__ x, const float* __restrict__ minuend, float* __restrict__ y,
-                                                          int planes, int h, int w) {
+__device__ __forceinline__ void pyr_up_quad_body(const float* __restrict__ x, const float* __restrict__ minuend, float* __restrict__ y,
+                                                 int planes, int h, int w, unsigned vblock, unsigned vgrid) {
     const unsigned total = static_cast<unsigned>(planes) * h * w;
     const int OW = 2 * w;
-    pdl_wait();
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    for (unsigned idx = vblock * blockDim.x + threadIdx.x; idx < total; idx += vgrid * blockDim.x) {
         const unsigned r = idx / static_cast<unsigned>(w);
         const int b = static_cast<int>(idx - r * w);
         const unsigned p = r / static_cast<unsigned>(h);
@@ -136,6 +141,31 @@ __global__ void __launch_bounds__(256) pyr_up_quad_kernel(const float* __restric
         *reinterpret_cast<float2*>(y + o0) = top;
         *reinterpret_cast<float2*>(y + o1) = bot;
     }
+}
+
+__global__ void __launch_bounds__(256) pyr_up_quad_kernel(const float* __restrict__ x, const float* __restrict__ minuend, float* __restrict__ y,
+                                                          int planes, int h, int w) {
+    pdl_wait();
+    pyr_up_quad_body(x, minuend, y, planes, h, w, blockIdx.x, gridDim.x);
+}
+
+// The residual of pyramid level l (pyr_up of its coarse image, subtracted from the level) and the coarse image of level l + 1 both
+// need only the coarse image of level l: one launch, the first up_blocks blocks on the residual, the rest on the next reduction.
+// A feed of four levels is then five launches instead of seven (the feed phase is bound by the host: ~4 us per launch).
+struct PyrPair {
+    const float* up_x;       // coarse image of level l: [planes, h, w]
+    const float* up_minuend; // level l: [planes, 2h, 2w]
+    float* up_y;             // residual of level l
+    float* down_y;           // coarse image of level l + 1: [planes, h / 2, w / 2] (its input is up_x)
+    int planes, h, w;
+    unsigned up_blocks;
+};
+__global__ void __launch_bounds__(256) pyr_pair_kernel(const PyrPair a) {
+    pdl_wait();
+    if (blockIdx.x < a.up_blocks)
+        pyr_up_quad_body(a.up_x, a.up_minuend, a.up_y, a.planes, a.h, a.w, blockIdx.x, a.up_blocks);
+    else
+        pyr_down_body(a.up_x, a.down_y, a.planes, a.h, a.w, (a.h + 1) / 2, (a.w + 1) / 2, blockIdx.x - a.up_blocks, gridDim.x - a.up_blocks);
 }
 
 // desc[m, c, i, j] = level[m / per_image, c, py[m] + j - half, px[m] + i - half]; per-channel sum / sum-of-squares.
@@ -495,25 +525,64 @@ extern "C" int bgan_swd_feed_f32(const float* minibatch, int n, int c, int h, in
     const int dlen = c * nhood * nhood;
     const bool fused_gather = levels <= kMaxFeedLevels && dlen <= 32 * 5 && c <= 4 && (nhood & 1) && nhoods_per_image > 0;
     ExtractLevels lv{};
-    float* next = static_cast<float*>(ws);
-    const float* cur = minibatch;  // Gaussian image of the current level
+    // Pyramid (:83-88): coarse(l) = pyr_down(g(l)), residual(l) = g(l) - pyr_up(coarse(l)), g(l + 1) = coarse(l).  residual(l)
+    // and coarse(l + 1) both need coarse(l) only and share a launch (pyr_pair_kernel) when the quad kernel applies.
+    const float* g[16];
+    float* resid[16];
+    float* coarse[16];
+    {
+        float* next = static_cast<float*>(ws);
+        const float* cur = minibatch;
+        for (int l = 0; l < levels; ++l) {
+            g[l] = cur;
+            resid[l] = coarse[l] = nullptr;
+            if (l < levels - 1) {
+                const size_t plane = static_cast<size_t>(n) * c * (h >> l) * (w >> l);
+                resid[l] = next;
+                coarse[l] = next + plane;
+                next = coarse[l] + plane / 4;
+                cur = coarse[l];
+            }
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int planes = n * c;
+    if (levels > 1) {
+        const int rc = bgan_pyr_down_f32(g[0], coarse[0], planes, h, w, stream);  // :85-86
+        if (rc) return rc;
+    }
+    for (int l = 0; l < levels - 1; ++l) {
+        const int hc = (h >> l) / 2, wc = (w >> l) / 2;  // coarse image of level l
+        const bool more = l + 1 < levels - 1;           // level l + 1 is reduced as well
+        const int64_t up_total = static_cast<int64_t>(planes) * hc * wc;
+        const bool pair_ok = more && hc >= 2 && wc >= 2 && reinterpret_cast<uintptr_t>(resid[l]) % 8 == 0 && reinterpret_cast<uintptr_t>(g[l]) % 8 == 0 &&
+                             up_total * 4 < (int64_t(1) << 31);
+        if (pair_ok) {
+            PyrPair a;
+            a.up_x = coarse[l];
+            a.up_minuend = g[l];
+            a.up_y = resid[l];
+            a.down_y = coarse[l + 1];
+            a.planes = planes;
+            a.h = hc;
+            a.w = wc;
+            a.up_blocks = grid_for(up_total, 256, 16);
+            const unsigned down_blocks = grid_for(static_cast<int64_t>(planes) * ((hc + 1) / 2) * ((wc + 1) / 2), 256, 16);
+            BGAN_CUDA_OK(launch_pdl(pyr_pair_kernel, dim3(a.up_blocks + down_blocks), dim3(256), 0, st, a));
+        } else {
+            int rc = bgan_pyr_up_f32(coarse[l], g[l], resid[l], planes, hc, wc, stream);  // :87  residual = g - pyr_up(down)
+            if (rc) return rc;
+            if (more) {
+                rc = bgan_pyr_down_f32(g[l + 1], coarse[l + 1], planes, hc, wc, stream);
+                if (rc) return rc;
+            }
+        }
+    }
     int hl = h, wl = w;
     for (int l = 0; l < levels; ++l) {
         const int32_t* px = positions + static_cast<int64_t>(2 * l) * count;
         const int32_t* py = px + count;
-        const float* level = cur;
-        if (l < levels - 1) {
-            const size_t plane = static_cast<size_t>(n) * c * hl * wl;
-            float* resid = next;
-            float* coarse = next + plane;
-            next = coarse + plane / 4;
-            int rc = bgan_pyr_down_f32(cur, coarse, n * c, hl, wl, stream);                       // :85-86
-            if (rc) return rc;
-            rc = bgan_pyr_up_f32(coarse, cur, resid, n * c, hl / 2, wl / 2, stream);              // :87  residual = g - pyr_up(down)
-            if (rc) return rc;
-            level = resid;
-            cur = coarse;
-        }
+        const float* level = l < levels - 1 ? resid[l] : g[l];
         BGAN_REQUIRE(hl >= nhood && wl >= nhood, BGAN_E_BADARG, "bgan_swd_feed_f32: level %d (%d x %d) smaller than the neighbourhood", l, hl, wl);
         if (fused_gather) {
             lv.level[l] = level;
