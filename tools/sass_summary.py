@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "blurred_gan_b200", "libbgan_b200.so")
 WATCH = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UTCATOMSWS", "SYNCS", "LDGSTS", "HMMA", "VOTE", "MATCH",
-         "ATOMS", "REDG", "ATOMG", "DFMA", "DADD", "FFMA"]
+         "ATOMS", "REDG", "ATOMG", "DFMA", "DADD", "FFMA2", "FFMA"]
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 kernels = collections.OrderedDict()
 cur = None
