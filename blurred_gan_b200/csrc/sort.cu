@@ -1,5 +1,7 @@
 // Segmented LSD radix sort of fp32 keys for sm_100a -- the np.sort(proj, axis=0) of the reference's
-// sliced_wasserstein.py:47-48, one segment per projection direction (direction-major layout).
+// sliced_wasserstein.py:47-48, one segment per projection direction (direction-major layout).  Since the end of round 2 this is
+// the sort of segments longer than 2^21 keys and the fall-back of the value-bucket sort (sort_sample.cu), which takes the rest;
+// the entry points at the bottom of this file choose.
 //
 // 4 passes of 8-bit digits over order-preserving uint32 images of the floats.  Per pass:
 //   hist    : per-(segment, tile) digit counts                       -> counts[seg][tile][digit]
@@ -350,7 +352,7 @@ static size_t lsd_workspace_bytes(int64_t rows, int segments) {
     return ((keys + 255) & ~size_t(255)) + 2 * counts + part;  // keys | counts | offsets | chunk partials
 }
 
-// Which sort runs: the splitter / shared-memory-bucket sort (sort_sample.cu) for segments it holds, else the radix passes below.
+// Which sort runs: the value-bucket sort (sort_sample.cu) for segments it holds, else the radix passes below.
 // BGAN_SORT_ALGO=lsd forces the radix sort (A/B measurements).
 static bool use_sample_sort(int64_t rows) {
     const char* algo = getenv("BGAN_SORT_ALGO");
@@ -419,7 +421,7 @@ static int sort_one(float* keys_device, int64_t rows, int segments, void* ws, cu
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         BGAN_CUDA_OK(cudaStreamIsCapturing(stream, &cap));
         const uint32_t* flag_device = nullptr;
-        if (cap == cudaStreamCaptureStatusNone || rows <= 8192) {
+        if (cap == cudaStreamCaptureStatusNone || rows <= 8192) {  // (<= 8192 keys: one CTA per segment, no flag, no read-back)
             const int rc = sample_sort_launch(keys_device, rows, segments, ws, stream, da, &flag_device);
             if (rc) return rc;
             g_sort_path = 2;

@@ -1,4 +1,4 @@
-// Shared between the two segmented sorts of fp32 keys (sort.cu: LSD radix; sort_sample.cu: splitters + shared-memory buckets).
+// Shared between the two segmented sorts of fp32 keys (sort.cu: LSD radix; sort_sample.cu: value buckets sorted in shared memory).
 #pragma once
 
 #include "common.cuh"

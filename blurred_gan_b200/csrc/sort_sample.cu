@@ -17,8 +17,8 @@
 //   scatter    per block: keys regrouped by id in shared memory (slot = local start + shared-memory atomic), written as
 //              runs to scratch.  Not stable -- the last step sorts the buckets anyway.
 //   local sort persistent CTAs take runs of adjacent buckets (<= 8192 keys): sub-bucket = linear map of the value between the
-//              run's bounds (~2 keys per sub-bucket), count with atomics, scan, place, then -- in slot order, so that neighbouring
-//              lanes read neighbouring words -- rank every key against the few keys of its sub-bucket and write it to its
+//              run's bounds (0.5 - 1 key per sub-bucket), count with atomics, scan, place, then -- in slot order, so that neighbouring
+//              lanes read neighbouring words -- rank every key against its sub-bucket (four unconditional probes) and write it to its
 //              final position (or, fused: meet the sorted A there and accumulate |a - b|).  A run whose sub-buckets are badly
 //              loaded (clustered values, non-finite bounds) is sorted by a bitonic network in shared memory instead: slower,
 //              never wrong.

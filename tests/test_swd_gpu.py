@@ -128,7 +128,7 @@ def test_projection_long_descriptors_use_the_fma_kernel():
 @pytest.mark.parametrize("segments,rows", [(1, 1), (3, 5), (2, 4096), (5, 4097), (130, 1000), (3, 8192), (3, 8193), (4, 100000), (4, 100001),
                                            (1, 1 << 20), (2, 1 << 21), (1, (1 << 21) + 1)])
 def test_segmented_sort_is_exact(segments, rows, algo, monkeypatch):
-    """Three routes: the splitter / shared-memory-bucket sort (segments of up to 2^21 keys), the radix passes alone, and the
+    """Three routes: the value-bucket sort (segments of up to 2^21 keys), the radix passes alone, and the
     radix passes entered through the sample sort's overflow flag."""
     from blurred_gan_b200 import _lib, ops
 
