@@ -151,8 +151,9 @@ int bgan_swd_project_last_path(void);
  * from the query below).  The order is that of the floats' order-preserving uint32 images: -0 before +0, NaNs with the sign
  * bit clear last (as np.sort), NaNs with the sign bit set first.
  * Segments of up to 2^21 keys are sorted by value buckets in shared memory (two passes over HBM: csrc/sort_sample.cu);
- * longer segments, and inputs whose values are so unevenly spread that a bucket does not fit a CTA (outliers tens of
- * standard deviations out, one value repeated thousands of times), by four LSD radix passes (csrc/sort.cu).  The second
+ * longer segments, and inputs whose values are so unevenly spread that a bucket does not fit a CTA (outliers hundreds of
+ * standard deviations out; up to 16 heavily repeated values per segment are recognised and cost nothing), by four LSD radix
+ * passes (csrc/sort.cu).  The second
  * case is detected on the device: for segments of more than 8192 keys the call therefore reads one 4-byte flag back and
  * SYNCHRONISES THE STREAM before it returns (a stream that is being captured takes the radix passes, which never do). */
 size_t bgan_swd_sort_workspace_bytes(int64_t rows, int segments);
