@@ -31,6 +31,7 @@
 // Segments of <= 8192 keys skip everything but the last step.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "sort.cuh"
 
@@ -220,22 +221,25 @@ __global__ void __launch_bounds__(kModelThreads) ss_model_kernel(const uint32_t*
         }
     }
     __syncthreads();
-    uint32_t tag_of[kPerThread];
+    const bool any_heavy = s_nheavy != 0;  // (uniform; smooth data: no cell is heavy and the three passes below are skipped)
+    if (any_heavy) {
+        uint32_t tag_of[kPerThread];
 #pragma unroll
-    for (int e = 0; e < kPerThread; ++e) {
-        const uint32_t i = static_cast<uint32_t>(e * kModelThreads + tid);
-        tag_of[e] = i < static_cast<uint32_t>(n) ? s_hist[cell_of[e]] >> 24 : 0u;
-        if (tag_of[e]) atomicMin(&s_hfirst[tag_of[e] - 1], i);
+        for (int e = 0; e < kPerThread; ++e) {
+            const uint32_t i = static_cast<uint32_t>(e * kModelThreads + tid);
+            tag_of[e] = i < static_cast<uint32_t>(n) ? s_hist[cell_of[e]] >> 24 : 0u;
+            if (tag_of[e]) atomicMin(&s_hfirst[tag_of[e] - 1], i);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < kPerThread; ++e)
+            if (tag_of[e] && s_hfirst[tag_of[e] - 1] == static_cast<uint32_t>(e * kModelThreads + tid)) s_hval[tag_of[e] - 1] = x[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < kPerThread; ++e)
+            if (tag_of[e] && __uint_as_float(x[e]) == __uint_as_float(s_hval[tag_of[e] - 1])) atomicAdd(&s_heq[tag_of[e] - 1], 1u);
+        __syncthreads();
     }
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < kPerThread; ++e)
-        if (tag_of[e] && s_hfirst[tag_of[e] - 1] == static_cast<uint32_t>(e * kModelThreads + tid)) s_hval[tag_of[e] - 1] = x[e];
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < kPerThread; ++e)
-        if (tag_of[e] && __uint_as_float(x[e]) == __uint_as_float(s_hval[tag_of[e] - 1])) atomicAdd(&s_heq[tag_of[e] - 1], 1u);
-    __syncthreads();
     if (tid < kSsMaxHeavy) {
         const bool tagged = static_cast<uint32_t>(tid) < min(s_nheavy, static_cast<uint32_t>(kSsMaxHeavy));
         const bool single = tagged && s_heq[tid] >= static_cast<uint32_t>(kSsHeavySamples);  // (a NaN candidate equals nothing)
@@ -305,8 +309,10 @@ __global__ void __launch_bounds__(kModelThreads) ss_model_kernel(const uint32_t*
     uint2* info = idinfo + static_cast<size_t>(seg) * ids;
     for (int id = tid; id < ids; id += kModelThreads) {
         uint32_t eq = 0;
+        if (any_heavy) {
 #pragma unroll
-        for (int k = 0; k < kSsMaxHeavy; ++k) eq |= (s_hid0[k] != 0xffffffffu && s_hid0[k] + 1 == static_cast<uint32_t>(id)) ? 1u : 0u;
+            for (int k = 0; k < kSsMaxHeavy; ++k) eq |= (s_hid0[k] != 0xffffffffu && s_hid0[k] + 1 == static_cast<uint32_t>(id)) ? 1u : 0u;
+        }
         info[id] = make_uint2(s_cell_lo[id] | (eq << 31), s_cell_hi[id]);
     }
     if (tid < kSsMaxHeavy)
@@ -326,7 +332,12 @@ __global__ void __launch_bounds__(kSsThreads) ss_classify_kernel(const uint32_t*
     uint32_t* hist = reinterpret_cast<uint32_t*>(s_cls + cells * sizeof(uint16_t));
     uint2* s_hv = reinterpret_cast<uint2*>(hist + n_ids);
     const int seg = blockIdx.y, tid = threadIdx.x;
-    if (tid < kSsMaxHeavy) s_hv[tid] = heavy[static_cast<size_t>(seg) * kSsMaxHeavy + tid];
+    bool mine_heavy = false;
+    if (tid < kSsMaxHeavy) {
+        s_hv[tid] = heavy[static_cast<size_t>(seg) * kSsMaxHeavy + tid];
+        mine_heavy = s_hv[tid].y != 0xffffffffu;
+    }
+    const bool seg_heavy = __syncthreads_or(mine_heavy) != 0;
     {
         const uint4* g = reinterpret_cast<const uint4*>(lut + static_cast<size_t>(seg) * cells);  // (cells is a multiple of 32)
         for (int i = tid; i < cells / 8; i += kSsThreads) reinterpret_cast<uint4*>(s_lut)[i] = __ldg(g + i);
@@ -343,29 +354,38 @@ __global__ void __launch_bounds__(kSsThreads) ss_classify_kernel(const uint32_t*
         const size_t at = static_cast<size_t>(seg) * rows + base;
         const uint32_t* src = keys + at;
         uint16_t* dst = ids + at;
-        auto one = [&](uint32_t bits) {
-            uint32_t id = s_lut[linear_cell(bits, lo, scale, cells)];
-            if (id & 0x8000u) {  // the cell of a heavy value: below it / the value / above it
-                const uint2 h = s_hv[id & 0x7fffu];
-                const float x = __uint_as_float(bits), v = __uint_as_float(h.x);
-                id = h.y + (x == v ? 1u : (x > v ? 2u : 0u));
-                if (x != x) id = (bits >> 31) ? h.y : h.y + 2u;
-            }
-            atomicAdd(&hist[id], 1u);
-            return id;
-        };
-        int done = 0;
-        if ((at & 3) == 0) {
-            const int vec = valid >> 2;
+        auto block = [&](auto heavy_tag) {  // (two bodies: segments without heavy values skip the test per key)
+            constexpr bool kHeavy = decltype(heavy_tag)::value;
+            auto one = [&](uint32_t bits) {
+                uint32_t id = s_lut[linear_cell(bits, lo, scale, cells)];
+                if constexpr (kHeavy) {
+                    if (id & 0x8000u) {  // the cell of a heavy value: below it / the value / above it
+                        const uint2 h = s_hv[id & 0x7fffu];
+                        const float x = __uint_as_float(bits), v = __uint_as_float(h.x);
+                        id = h.y + (x == v ? 1u : (x > v ? 2u : 0u));
+                        if (x != x) id = (bits >> 31) ? h.y : h.y + 2u;
+                    }
+                }
+                atomicAdd(&hist[id], 1u);
+                return id;
+            };
+            int done = 0;
+            if ((at & 3) == 0) {
+                const int vec = valid >> 2;
 #pragma unroll 4
-            for (int v = tid; v < vec; v += kSsThreads) {
-                const uint4 k = __ldg(reinterpret_cast<const uint4*>(src) + v);
-                const uint32_t i0 = one(k.x), i1 = one(k.y), i2 = one(k.z), i3 = one(k.w);
-                reinterpret_cast<uint2*>(dst)[v] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
+                for (int v = tid; v < vec; v += kSsThreads) {
+                    const uint4 k = __ldg(reinterpret_cast<const uint4*>(src) + v);
+                    const uint32_t i0 = one(k.x), i1 = one(k.y), i2 = one(k.z), i3 = one(k.w);
+                    reinterpret_cast<uint2*>(dst)[v] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
+                }
+                done = vec << 2;
             }
-            done = vec << 2;
-        }
-        for (int i = done + tid; i < valid; i += kSsThreads) dst[i] = static_cast<uint16_t>(one(__ldg(src + i)));
+            for (int i = done + tid; i < valid; i += kSsThreads) dst[i] = static_cast<uint16_t>(one(__ldg(src + i)));
+        };
+        if (seg_heavy)
+            block(std::true_type{});
+        else
+            block(std::false_type{});
         __syncthreads();
         uint16_t* c = counts + (static_cast<size_t>(seg) * blocks + blk) * n_ids;
         for (int j = tid; j < n_ids; j += kSsThreads) c[j] = static_cast<uint16_t>(hist[j]);
